@@ -1,0 +1,64 @@
+"""ctypes binding of libdvst.so (the C ABI declared in include/dvst.h).
+
+The product path has no CPU / PyTorch fallback: if the shared library is missing, `lib()` raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdvst.so")
+
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_float = ctypes.c_float
+
+
+class DvstError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); kept in one table so tests can check every symbol of include/dvst.h is exported.
+SIGNATURES = {
+    "dvst_last_error": (ctypes.c_char_p, []),
+    "dvst_launch_count": (c_ll, []),
+    "dvst_abi_version": (c_int, []),
+    "dvst_gemm_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
+                               c_void_p, c_ll, c_int, c_ll, c_int, c_void_p]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DvstError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the CUDA path)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DvstError(lib().dvst_last_error().decode())
+
+
+def launch_count():
+    return int(lib().dvst_launch_count())
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,333 @@
+// Persistent, warp-specialised tcgen05/TMEM GEMM for sm_100a.
+//
+//   out[M,N] = epilogue( A[M,K] (bf16, row-major)  x  W[N,K]^T (bf16, row-major = nn.Linear layout) )
+//
+// Replaces every nn.Linear on the reference hot path (models/timesformer.py:41-52,63-64,71,83,108,133 and
+// vision_transformer.py:254-266): both operands are K-major, so they are staged by TMA (SWIZZLE_128B) and fed
+// to tcgen05.mma without any transpose.  Accumulators live in TMEM (2 x 256 fp32 columns, double buffered so the
+// epilogue of tile i overlaps the MMAs of tile i+1).
+//
+// Warp roles (384 threads, 1 CTA / SM, grid = #SMs, static round-robin tile schedule):
+//   warp 0      : TMA producer (one lane)       - 4-stage ring of {A 128x64, W 256x64} bf16 tiles (48 KiB / stage)
+//   warp 1      : MMA issuer (one lane)         - 4 x tcgen05.mma 128x256x16 per stage, tcgen05.commit -> mbarriers
+//   warp 2      : TMEM allocator / deallocator
+//   warps 4..11 : epilogue                      - tcgen05.ld 32x32b.x32 -> bias / GELU -> per-warp smem transpose ->
+//                                                 coalesced residual read + store (fp32, bf16, or bf16 hi/lo pair)
+//
+// `split` mode: A and W hold [hi | lo] bf16 halves along K (lo at column offset K); the K loop then runs the three
+// products hi*hi, hi*lo, lo*hi into the same accumulator (~16 mantissa bits) - the "precision=high" path that
+// reference-exact scoring (dino_similarity.py:59-63, tau_t = 0.02) needs.
+#include "dvst_internal.h"
+#include "ptx.cuh"
+
+namespace dvst {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int EPI_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 4;
+constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STG_STRIDE = 20;  // fp32 words per staged row (16 payload + 4 pad): conflict-free 128-bit STS/LDS
+constexpr int STG_BYTES = 32 * STG_STRIDE * 4;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256 /*barriers*/;
+
+struct GemmParams {
+  int M, N, K;
+  int split;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  void* out;
+  long long ldo;
+  int out_kind;  // 0 = bf16, 1 = fp32, 2 = bf16 hi/lo pair (lo at column + lo_off)
+  long long lo_off;
+  int act;  // 0 = none, 1 = exact-erf GELU
+  int num_m_blocks, num_n_blocks;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * A_BYTES;
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES;
+  const uint32_t full_bar = bars;                       // [STAGES]
+  const uint32_t empty_bar = bars + 8 * STAGES;         // [STAGES]
+  const uint32_t tfull_bar = bars + 16 * STAGES;        // [ACC_STAGES]
+  const uint32_t tempty_bar = tfull_bar + 8 * ACC_STAGES;
+  const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 16 * STAGES +
+                                           16 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_slot, TMEM_COLS);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int nk = p.K / BK;
+  const int num_iters = p.split ? 3 * nk : nk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks;
+        const int n_blk = tile % p.num_n_blocks;
+        for (int it = 0; it < num_iters; ++it) {
+          int ka, kb;
+          if (p.split) {
+            const int kblk = it / 3, term = it - 3 * kblk;  // 0: hi*hi, 1: hi*lo, 2: lo*hi
+            ka = kblk * BK + (term == 2 ? p.K : 0);
+            kb = kblk * BK + (term == 1 ? p.K : 0);
+          } else {
+            ka = kb = it * BK;
+          }
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+          tma_load_2d(sA + s * A_BYTES, &tmA, full_bar + 8 * s, ka, m_blk * BM);
+          tma_load_2d(sB + s * B_BYTES, &tmB, full_bar + 8 * s, kb, n_blk * BN);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + 8 * a, aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + a * BN;
+        for (int it = 0; it < num_iters; ++it) {
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = sA + s * A_BYTES;
+          const uint32_t b_addr = sB + s * B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16<1>(tmem_d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                         idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * a);
+        if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= FIRST_EPI_WARP) {
+    const int e = warp - FIRST_EPI_WARP;
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int half = e >> 2;  // which 128-column half of the accumulator
+    float* stg = stg_all + e * (32 * STG_STRIDE);
+    int a = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile % p.num_n_blocks;
+      mbar_wait(tfull_bar + 8 * a, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = half * 128 + c * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col0, v);
+        tmem_ld_wait();
+        float f[32];
+        const int gcol0 = n_blk * BN + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + gcol0 + j);
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4* dst = reinterpret_cast<float4*>(stg + lane * STG_STRIDE);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            dst[j4] = make_float4(f[16 * h + 4 * j4], f[16 * h + 4 * j4 + 1], f[16 * h + 4 * j4 + 2],
+                                  f[16 * h + 4 * j4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane & 7);
+            const int cg = lane >> 3;
+            float4 val = *reinterpret_cast<const float4*>(stg + row * STG_STRIDE + cg * 4);
+            const long long grow = static_cast<long long>(m_blk) * BM + q * 32 + row;
+            const int gcol = gcol0 + 16 * h + cg * 4;
+            if (grow < p.M) {
+              if (p.residual != nullptr) {
+                const float4 r = *reinterpret_cast<const float4*>(p.residual + grow * p.ldr + gcol);
+                val.x += r.x; val.y += r.y; val.z += r.z; val.w += r.w;
+              }
+              if (p.out_kind == 1) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.ldo + gcol) = val;
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldo + gcol;
+                const uint32_t h0 = pack_bf16x2(val.x, val.y), h1 = pack_bf16x2(val.z, val.w);
+                *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
+                if (p.out_kind == 2) {
+                  const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&h0);
+                  const __nv_bfloat162 b1 = *reinterpret_cast<const __nv_bfloat162*>(&h1);
+                  const uint32_t l0 = pack_bf16x2(val.x - __low2float(b0), val.y - __high2float(b0));
+                  const uint32_t l1 = pack_bf16x2(val.z - __low2float(b1), val.w - __high2float(b1));
+                  *reinterpret_cast<uint2*>(o + p.lo_off) = make_uint2(l0, l1);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * a);
+      if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error("cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (code %d)", static_cast<int>(r));
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  if (g.M <= 0) return 0;
+  if (g.N % BN != 0) return set_error("gemm: N=%d must be a multiple of %d", g.N, BN);
+  if (g.K % BK != 0) return set_error("gemm: K=%d must be a multiple of %d", g.K, BK);
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15) || (g.lda % 8) ||
+      (g.ldw % 8))
+    return set_error("gemm: operands must be 16-byte aligned with leading dimensions multiple of 8");
+  if (g.out_kind < 0 || g.out_kind > 2) return set_error("gemm: bad out_kind %d", g.out_kind);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+
+  const uint64_t kcols = static_cast<uint64_t>(g.K) * (g.split ? 2 : 1);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, kcols, g.lda, BM, BK)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmB, g.W, g.N, kcols, g.ldw, BN, BK)) return rc;
+
+  GemmParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.split = g.split;
+  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr;
+  p.out = g.out; p.ldo = g.ldo; p.out_kind = g.out_kind; p.lo_off = g.lo_off; p.act = g.act;
+  p.num_m_blocks = (g.M + BM - 1) / BM;
+  p.num_n_blocks = g.N / BN;
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+}  // namespace dvst
