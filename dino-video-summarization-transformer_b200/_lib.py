@@ -27,6 +27,18 @@ SIGNATURES = {
     "dvst_abi_version": (c_int, []),
     "dvst_gemm_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
                                c_void_p, c_ll, c_int, c_ll, c_int, c_void_p]),
+    "dvst_create": (c_int, [c_void_p, c_void_p]),
+    "dvst_destroy": (None, [c_void_p]),
+    "dvst_set_weight": (c_int, [c_void_p, ctypes.c_char_p, c_void_p]),
+    "dvst_finalize_weights": (c_int, [c_void_p]),
+    "dvst_workspace_bytes": (c_ll, [c_void_p, c_int, c_int, c_int, c_int]),
+    "dvst_forward_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_ll,
+                                      c_void_p]),
+    "dvst_pair_loss": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_float, c_float, c_int, c_int, c_void_p,
+                               c_void_p]),
+    "dvst_layernorm768": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_float,
+                                  c_void_p]),
+    "dvst_attention": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p]),
 }
 
 

@@ -41,4 +41,23 @@ int dvst_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, c
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
+int dvst_pair_loss(const float* student, long long lds, const float* teacher, long long ldt, const float* center,
+                   float teacher_temp, float student_temp, int dim, int pairs, float* loss, void* stream) {
+  if (dim <= 0 || pairs < 0) return set_error("dvst_pair_loss: bad dim %d / pairs %d", dim, pairs);
+  if (teacher_temp <= 0.f || student_temp <= 0.f) return set_error("dvst_pair_loss: temperatures must be > 0");
+  return launch_pair_loss(student, lds, teacher, ldt, center, teacher_temp, student_temp, dim, pairs, loss,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,
+                      int out_kind, long long lo_off, long long M, float eps, void* stream) {
+  return launch_layernorm768(x, ldx, gamma, beta, out, ldo, out_kind, lo_off, M, eps,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int dvst_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                   int N, long long cls_base, void* stream) {
+  return launch_attention(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, 0, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -1,0 +1,295 @@
+// Fused softmax(q k^T / 8) v for the TimeSformer token layout (models/timesformer.py:68-87 as called from
+// Block.forward :124-185), reading q/k/v straight out of the packed qkv GEMM output [rows, 2304] bf16 in the resident
+// (b, n, t) row order - none of the reference's rearrange / permute / cat copies are materialised:
+//
+//   TEMPORAL : one sequence per (b, n)  = the T consecutive rows  (b*N + n)*T + t            (:130-131)
+//   SPATIAL  : one sequence per (b, t)  = CLS row (cls_base + b) followed by the N rows (b*N + n)*T + t, i.e. a
+//              stride-T gather; the CLS query's output goes to cls_out[b, t, :] (fp32) for the mean over frames (:140-164)
+//   JOINT    : one sequence per b       = CLS row followed by the N*T rows b*N*T + i          (:120-123)
+//
+// Flash-style: K/V of one (sequence, head) are staged once in shared memory (XOR-swizzled 16-byte chunks), each warp
+// owns 16-query tiles, scores never leave registers (online softmax over 64-key blocks, exp2 with folded scale).
+// Math runs on mma.sync m16n8k16 bf16 (fp32 accumulate); attention is ~3.4 % of the path's FLOPs.
+#include "dvst_internal.h"
+#include "ptx.cuh"
+
+namespace dvst {
+
+namespace {
+
+constexpr int HD = 64;     // head dim
+constexpr int QKV_LD = 2304;
+constexpr int DMODEL = 768;
+
+struct AttnParams {
+  const __nv_bfloat16* qkv;  // [rows, ld]
+  long long ld;              // row stride of qkv (2304, or 4608 when hi/lo pairs are stored)
+  __nv_bfloat16* out;        // [rows, ldo]
+  long long ldo;
+  float* cls_out;            // SPATIAL: [B, T, 768] fp32
+  int mode;                  // 0 temporal, 1 spatial, 2 joint, 3 space-only
+  int S;                     // sequence length
+  int n_seq;                 // number of sequences
+  int T, N;
+  long long cls_base;        // row index of the first CLS row
+  int heads;
+  int split;                 // also write the bf16 rounding residual (lo) at column + lo_off
+  long long lo_off;
+};
+
+__device__ __forceinline__ long long row_of(const AttnParams& p, int seq, int i) {
+  if (p.mode == 0) return static_cast<long long>(seq) * p.T + i;
+  if (p.mode == 1) {
+    const int b = seq / p.T, t = seq - b * p.T;
+    return i == 0 ? p.cls_base + b : (static_cast<long long>(b) * p.N + (i - 1)) * p.T + t;
+  }
+  if (p.mode == 2) return i == 0 ? p.cls_base + seq : static_cast<long long>(seq) * p.N * p.T + (i - 1);
+  {  // mode 3: space-only, sequence (b, t) with its own CLS row cls_base + b*T + t
+    const int b = seq / p.T, t = seq - b * p.T;
+    return i == 0 ? p.cls_base + seq : (static_cast<long long>(b) * p.N + (i - 1)) * p.T + t;
+  }
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// WPP = warps per problem (4: spatial / joint, 1: temporal).  CTA = 4 warps.
+template <int WPP>
+__global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  constexpr int PPC = 4 / WPP;  // problems per CTA
+  const int S = p.S;
+  const int S_pad = (S + 15) & ~15;
+  const long long prob = static_cast<long long>(blockIdx.x) * PPC + warp / WPP;
+  const long long n_prob = static_cast<long long>(p.n_seq) * p.heads;
+  const bool active = prob < n_prob;
+  const int seq = active ? static_cast<int>(prob / p.heads) : 0;
+  const int head = active ? static_cast<int>(prob % p.heads) : 0;
+
+  uint8_t* sK = smem + static_cast<size_t>(warp / WPP) * (2 * S_pad * 128);
+  uint8_t* sV = sK + S_pad * 128;
+  const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+
+  // ---- stage K and V (16-byte chunks, chunk index XOR (key & 7)) ----
+  {
+    const int nthr = WPP * 32;
+    const int tid = (warp % WPP) * 32 + lane;
+    const int total = S_pad * 8;
+    for (int idx = tid; idx < total; idx += nthr) {
+      const int key = idx >> 3, ch = idx & 7;
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (active && key < S) {
+        const __nv_bfloat16* src = p.qkv + row_of(p, seq, key) * p.ld + head * HD + ch * 8;
+        kv = __ldg(reinterpret_cast<const uint4*>(src + DMODEL));
+        vv = __ldg(reinterpret_cast<const uint4*>(src + 2 * DMODEL));
+      }
+      const int off = key * 128 + ((ch ^ (key & 7)) << 4);
+      *reinterpret_cast<uint4*>(sK + off) = kv;
+      *reinterpret_cast<uint4*>(sV + off) = vv;
+    }
+  }
+  if (WPP == 1) __syncwarp(); else __syncthreads();
+  if (!active) return;
+
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+  const int n_qtiles = S_pad >> 4;
+  const int n_kblocks = (S + 63) >> 6;
+
+  for (int qt = warp % WPP; qt < n_qtiles; qt += WPP) {
+    const int r0 = qt * 16 + g, r1 = r0 + 8;
+    // ---- Q fragments straight from global (each row's 64-wide head slice is 128 contiguous bytes) ----
+    uint32_t qa[4][4];
+    {
+      const __nv_bfloat16* q0 = p.qkv + row_of(p, seq, r0 < S ? r0 : 0) * p.ld + head * HD;
+      const __nv_bfloat16* q1 = p.qkv + row_of(p, seq, r1 < S ? r1 : 0) * p.ld + head * HD;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int c = kk * 16 + tig * 2;
+        qa[kk][0] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c)) : 0u;
+        qa[kk][1] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c)) : 0u;
+        qa[kk][2] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c + 8)) : 0u;
+        qa[kk][3] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c + 8)) : 0u;
+      }
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int kb = 0; kb < n_kblocks; ++kb) {
+      const int key0 = kb * 64;
+      const int ntile_pairs = min(4, (S_pad - key0) >> 4);  // 16-key groups present in this block
+      float s[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+      // ---- S = Q K^T ----
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        if (np < ntile_pairs) {
+          const int mat = lane >> 3, r = lane & 7;
+          const int key = key0 + np * 16 + (mat >> 1) * 8 + r;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int ch = kk * 2 + (mat & 1);
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(sK_u + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
+            mma_bf16(s[2 * np], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);
+            mma_bf16(s[2 * np + 1], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b2, b3);
+          }
+        }
+      }
+      // ---- mask + online softmax ----
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = key0 + nt * 8 + tig * 2;
+        if (c >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (c + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every block holds >= 1 valid key
+      const float c0 = exp2f((m0 - mn0) * scale_log2), c1 = exp2f((m1 - mn1) * scale_log2);
+      m0 = mn0; m1 = mn1;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = exp2f((s[nt][0] - mn0) * scale_log2);
+        s[nt][1] = exp2f((s[nt][1] - mn0) * scale_log2);
+        s[nt][2] = exp2f((s[nt][2] - mn1) * scale_log2);
+        s[nt][3] = exp2f((s[nt][3] - mn1) * scale_log2);
+        rs0 += s[nt][0] + s[nt][1];
+        rs1 += s[nt][2] + s[nt][3];
+      }
+      l0 = l0 * c0 + rs0;
+      l1 = l1 * c1 + rs1;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
+      // ---- O += P V ----
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (kk < ntile_pairs) {
+          const uint32_t a0 = pack2(s[2 * kk][0], s[2 * kk][1]), a1 = pack2(s[2 * kk][2], s[2 * kk][3]);
+          const uint32_t a2 = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+          const int mat = lane >> 3, r = lane & 7;
+          const int key = key0 + kk * 16 + (mat & 1) * 8 + r;
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
+            const int ch = dp * 2 + (mat >> 1);
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(sV_u + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
+            mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);
+            mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+          }
+        }
+      }
+    }
+    // ---- finalize: quad-reduce the row sums, normalise, store ----
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = half == 0 ? r0 : r1;
+      if (r >= S) continue;
+      const float inv = half == 0 ? inv0 : inv1;
+      if (p.mode == 1 && r == 0) {
+        const int b = seq / p.T, t = seq - b * p.T;
+        float* dst = p.cls_out + (static_cast<long long>(b) * p.T + t) * DMODEL + head * HD;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt)
+          *reinterpret_cast<float2*>(dst + dt * 8 + tig * 2) =
+              make_float2(o[dt][2 * half] * inv, o[dt][2 * half + 1] * inv);
+      } else {
+        __nv_bfloat16* dst = p.out + row_of(p, seq, r) * p.ldo + head * HD;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+          const float v0 = o[dt][2 * half] * inv, v1 = o[dt][2 * half + 1] * inv;
+          const uint32_t hi = pack2(v0, v1);
+          *reinterpret_cast<uint32_t*>(dst + dt * 8 + tig * 2) = hi;
+          if (p.split) {
+            const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hi);
+            *reinterpret_cast<uint32_t*>(dst + p.lo_off + dt * 8 + tig * 2) =
+                pack2(v0 - __low2float(hb), v1 - __high2float(hb));
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                     int N, long long cls_base, int split, cudaStream_t st) {
+  AttnParams p;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  p.ld = ld;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.cls_out = cls_out;
+  p.mode = mode;
+  p.T = T; p.N = N; p.cls_base = cls_base; p.heads = 12;
+  p.split = split; p.lo_off = DMODEL;
+  if (mode == 0) { p.S = T; p.n_seq = B * N; }
+  else if (mode == 1) { p.S = N + 1; p.n_seq = B * T; }
+  else if (mode == 2) { p.S = N * T + 1; p.n_seq = B; }
+  else if (mode == 3) { p.S = N + 1; p.n_seq = B * T; }
+  else return set_error("attention: bad mode %d", mode);
+  if (p.n_seq <= 0) return 0;
+  const int S_pad = (p.S + 15) & ~15;
+  const long long n_prob = static_cast<long long>(p.n_seq) * p.heads;
+  cudaError_t e;
+  if (mode == 0) {
+    const size_t smem = static_cast<size_t>(4) * 2 * S_pad * 128;
+    if (smem > 200 * 1024) return set_error("temporal attention: T=%d too long for the per-warp K/V staging", T);
+    static size_t cur = 0;
+    if (smem > cur) {
+      e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return set_error("attention attr: %s", cudaGetErrorString(e));
+      cur = smem;
+    }
+    attention_kernel<1><<<static_cast<unsigned>((n_prob + 3) / 4), 128, smem, st>>>(p);
+  } else {
+    const size_t smem = static_cast<size_t>(2) * S_pad * 128;
+    if (smem > 220 * 1024)
+      return set_error("attention: sequence of %d tokens does not fit the shared-memory K/V staging (max 880)", p.S);
+    static size_t cur = 0;
+    if (smem > cur) {
+      e = cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return set_error("attention attr: %s", cudaGetErrorString(e));
+      cur = smem;
+    }
+    attention_kernel<4><<<static_cast<unsigned>(n_prob), 128, smem, st>>>(p);
+  }
+  count_launch();
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : set_error("attention launch: %s", cudaGetErrorString(e));
+}
+
+}  // namespace dvst

@@ -1,0 +1,263 @@
+// HBM-bound kernels of the path: LayerNorm (fp32 residual stream -> bf16 GEMM operand), im2col for the patch
+// embedding, CLS-row handling, and the mode-R DINO loss.  All use one warp per 768-wide row, 128-bit coalesced
+// accesses and warp-shuffle reductions.
+#include "dvst_internal.h"
+#include "ptx.cuh"
+
+namespace dvst {
+
+namespace {
+
+constexpr int D = 768;
+constexpr int VEC_PER_LANE = D / (32 * 4);  // 6 float4 per lane
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// LayerNorm over rows of 768 fp32 (eps inside the sqrt, biased variance: torch.nn.LayerNorm, timesformer.py:596).
+// out_kind 0: bf16 [M, ldo]; 1: fp32 [M, ldo]; 2: bf16 hi at col, lo at col + lo_off.
+__global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ x, long long ldx,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, void* __restrict__ out,
+                                                           long long ldo, int out_kind, long long lo_off,
+                                                           long long M, float eps, long long rm_group,
+                                                           long long rm_stride, long long rm_offset) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  // optional output row remap: orow = (row / group) * stride + offset + row % group
+  const long long orow = rm_group > 0 ? (row / rm_group) * rm_stride + rm_offset + row % rm_group : row;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[VEC_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < VEC_PER_LANE; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    float4 y;
+    y.x = v[i].x * rstd * g.x + b.x;
+    y.y = v[i].y * rstd * g.y + b.y;
+    y.z = v[i].z * rstd * g.z + b.z;
+    y.w = v[i].w * rstd * g.w + b.w;
+    const int col = (lane + 32 * i) * 4;
+    if (out_kind == 1) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow * ldo + col) = y;
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + orow * ldo + col;
+      *reinterpret_cast<uint2*>(o) = make_uint2(pack2(y.x, y.y), pack2(y.z, y.w));
+      if (out_kind == 2) {
+        *reinterpret_cast<uint2*>(o + lo_off) =
+            make_uint2(pack2(y.x - bf16_round(y.x), y.y - bf16_round(y.y)),
+                       pack2(y.z - bf16_round(y.z), y.w - bf16_round(y.w)));
+      }
+    }
+  }
+}
+
+// im2col for Conv2d(k=16, s=16) (PatchEmbed, timesformer.py:201-208): x [B,3,T,H,W] fp32 -> rows (b, n, t) in the
+// resident token order, 768 columns in (c, ky, kx) order = the flattened conv weight's K order.
+// One thread moves 8 consecutive kx (two float4 loads, one 16-byte bf16 store).
+__global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                       long long ldo, int split, long long lo_off, int B, int T,
+                                                       int H, int W, int gh, int gw) {
+  const long long total = static_cast<long long>(B) * gh * gw * T * 96;  // 96 chunks of 8 per row
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunk = static_cast<int>(idx % 96);
+  const long long row = idx / 96;
+  const int t = static_cast<int>(row % T);
+  const long long bn = row / T;
+  const int n = static_cast<int>(bn % (gh * gw));
+  const int b = static_cast<int>(bn / (gh * gw));
+  const int c = chunk / 32, rem = chunk % 32, ky = rem / 2, kx0 = (rem % 2) * 8;
+  const int py = n / gw, px = n % gw;
+  const float* src =
+      x + (((static_cast<long long>(b) * 3 + c) * T + t) * H + (py * 16 + ky)) * W + px * 16 + kx0;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(src));
+  const float4 a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  __nv_bfloat16* o = out + row * ldo + chunk * 8;
+  *reinterpret_cast<uint4*>(o) = make_uint4(pack2(a0.x, a0.y), pack2(a0.z, a0.w), pack2(a1.x, a1.y), pack2(a1.z, a1.w));
+  if (split) {
+    *reinterpret_cast<uint4*>(o + lo_off) =
+        make_uint4(pack2(a0.x - bf16_round(a0.x), a0.y - bf16_round(a0.y)),
+                   pack2(a0.z - bf16_round(a0.z), a0.w - bf16_round(a0.w)),
+                   pack2(a1.x - bf16_round(a1.x), a1.y - bf16_round(a1.y)),
+                   pack2(a1.z - bf16_round(a1.z), a1.w - bf16_round(a1.w)));
+  }
+}
+
+// emb[n*T + t, :] = pos_embed[1 + pi(n)] + time_embed[tau(t)]: the additive embedding of every patch token
+// (timesformer.py:288-323), with the reference's nearest-neighbour resizes (F.interpolate(mode='nearest'), :292-303
+// and :314-318) evaluated exactly like ATen: src = min(floor(dst * float(src_len)/float(dst_len)), src_len - 1).
+__global__ void embed_table_kernel(const float* __restrict__ pos, int P, const float* __restrict__ time_embed, int T0,
+                                   float* __restrict__ out, int gh_eff, int gw, int N, int T) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(N) * T * (D / 4)) return;
+  const int c = static_cast<int>(idx % (D / 4));
+  const long long row = idx / (D / 4);
+  const int t = static_cast<int>(row % T), n = static_cast<int>(row / T);
+  int src_n = n;
+  if (N != P * P) {
+    const int py = n / gw, px = n % gw;
+    const float sy = static_cast<float>(P) / static_cast<float>(gh_eff), sx = static_cast<float>(P) / static_cast<float>(gw);
+    const int iy = min(static_cast<int>(floorf(py * sy)), P - 1), ix = min(static_cast<int>(floorf(px * sx)), P - 1);
+    src_n = iy * P + ix;
+  }
+  float4 v = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(1 + src_n) * D) + c);
+  if (time_embed != nullptr) {
+    int st = t;
+    if (T != T0) st = min(static_cast<int>(floorf(t * (static_cast<float>(T0) / static_cast<float>(T)))), T0 - 1);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(time_embed + static_cast<long long>(st) * D) + c);
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  reinterpret_cast<float4*>(out)[idx] = v;
+}
+
+// rows[r, :] = src[:] for r in [0, nrows): broadcast of cls_token + pos_embed[0] into the CLS rows (timesformer.py:310).
+__global__ void broadcast_row768_kernel(const float* __restrict__ src, float* __restrict__ dst, long long ldd,
+                                        int nrows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nrows * (D / 4)) return;
+  const int r = idx / (D / 4), c = idx % (D / 4);
+  reinterpret_cast<float4*>(dst + r * ldd)[c] = __ldg(reinterpret_cast<const float4*>(src) + c);
+}
+
+// out[b, :] = mean_t in[b, t, :]  (CLS residual averaged over frames, timesformer.py:162-164; the projection is
+// linear so the mean is taken BEFORE attn.proj).  Output bf16 (+ lo).
+__global__ void cls_mean_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long ldo, int split,
+                                long long lo_off, long long B, int T, float* __restrict__ out_f32) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const long long b = idx / D;
+  const int c = static_cast<int>(idx % D);
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += in[(b * T + t) * D + c];
+  s /= static_cast<float>(T);
+  if (out_f32 != nullptr) { out_f32[b * D + c] = s; return; }
+  const __nv_bfloat16 h = __float2bfloat16_rn(s);
+  out[b * ldo + c] = h;
+  if (split) out[b * ldo + lo_off + c] = __float2bfloat16_rn(s - __bfloat162float(h));
+}
+
+// Scoring DINOLoss (dino_similarity.py:129-135) for `pairs` (student, teacher) rows of `dim` fp32 values:
+//   loss = logsumexp(s/ts) - sum_j softmax((t - c)/tt)_j * s_j/ts.        One warp per pair.
+__global__ void __launch_bounds__(128) pair_loss_kernel(const float* __restrict__ s, long long lds,
+                                                        const float* __restrict__ t, long long ldt,
+                                                        const float* __restrict__ center, float inv_tt, float inv_ts,
+                                                        int dim, int pairs, float* __restrict__ loss) {
+  const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (p >= pairs) return;
+  const int lane = threadIdx.x & 31;
+  const float* sr = s + p * lds;
+  const float* tr = t + p * ldt;
+  float ms = -INFINITY, mt = -INFINITY;
+  for (int j = lane; j < dim; j += 32) {
+    ms = fmaxf(ms, sr[j] * inv_ts);
+    mt = fmaxf(mt, (tr[j] - (center ? center[j] : 0.f)) * inv_tt);
+  }
+  ms = warp_max(ms);
+  mt = warp_max(mt);
+  float zs = 0.f, zt = 0.f, cross = 0.f;
+  for (int j = lane; j < dim; j += 32) {
+    const float sv = sr[j] * inv_ts;
+    const float e = expf((tr[j] - (center ? center[j] : 0.f)) * inv_tt - mt);
+    zs += expf(sv - ms);
+    zt += e;
+    cross += e * sv;
+  }
+  zs = warp_sum(zs);
+  zt = warp_sum(zt);
+  cross = warp_sum(cross);
+  if (lane == 0) loss[p] = (ms + logf(zs)) - cross / zt;
+}
+
+}  // namespace
+
+int launch_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
+                        long long ldo, int out_kind, long long lo_off, long long M, float eps, cudaStream_t st,
+                        long long rm_group, long long rm_stride, long long rm_offset) {
+  if (M <= 0) return 0;
+  const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+  layernorm768_kernel<<<grid, 256, 0, st>>>(x, ldx, gamma, beta, out, ldo, out_kind, lo_off, M, eps, rm_group,
+                                            rm_stride, rm_offset);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("layernorm launch failed");
+}
+
+int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,
+                    cudaStream_t st) {
+  if (H % 16 || W % 16) return set_error("im2col: H, W must be multiples of 16 (got %d x %d)", H, W);
+  if (W % 4) return set_error("im2col: W must be a multiple of 4");
+  const int gh = H / 16, gw = W / 16;
+  const long long total = static_cast<long long>(B) * gh * gw * T * 96;
+  if (total == 0) return 0;
+  im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, H, W, gh, gw);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("im2col launch failed");
+}
+
+int launch_embed_table(const float* pos, int P, const float* time_embed, int T0, float* out, int gh, int gw, int T,
+                       cudaStream_t st) {
+  const int N = gh * gw;
+  const int gh_eff = (N + 1) / gw;  // the reference derives the target grid height as x.size(1) // W (:297)
+  const long long total = static_cast<long long>(N) * T * (D / 4);
+  if (total <= 0) return 0;
+  embed_table_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(pos, P, time_embed, T0, out, gh_eff, gw,
+                                                                               N, T);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("embed_table launch failed");
+}
+
+int launch_broadcast_row768(const float* src, float* dst, long long ldd, int nrows, cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  const int total = nrows * (D / 4);
+  broadcast_row768_kernel<<<(total + 255) / 256, 256, 0, st>>>(src, dst, ldd, nrows);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("broadcast_row launch failed");
+}
+
+int launch_cls_mean(const float* in, void* out, long long ldo, int split, long long lo_off, long long B, int T,
+                    float* out_f32, cudaStream_t st) {
+  if (B <= 0) return 0;
+  cls_mean_kernel<<<static_cast<unsigned>((B * D + 255) / 256), 256, 0, st>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, out_f32);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("cls_mean launch failed");
+}
+
+int launch_pair_loss(const float* s, long long lds, const float* t, long long ldt, const float* center, float tt,
+                     float ts, int dim, int pairs, float* loss, cudaStream_t st) {
+  if (pairs <= 0) return 0;
+  pair_loss_kernel<<<(pairs + 3) / 4, 128, 0, st>>>(s, lds, t, ldt, center, 1.0f / tt, 1.0f / ts, dim, pairs, loss);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("pair_loss launch failed");
+}
+
+}  // namespace dvst

@@ -46,6 +46,7 @@ struct GemmParams {
   const float* bias;
   const float* residual;
   long long ldr;
+  long long res_mod;  // > 0: residual row = row % res_mod (periodic table)
   void* out;
   long long ldo;
   int out_kind;  // 0 = bf16, 1 = fp32, 2 = bf16 hi/lo pair (lo at column + lo_off)
@@ -210,7 +211,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int gcol = gcol0 + 16 * h + cg * 4;
             if (grow < p.M) {
               if (p.residual != nullptr) {
-                const float4 r = *reinterpret_cast<const float4*>(p.residual + grow * p.ldr + gcol);
+                const long long rrow = p.res_mod > 0 ? grow % p.res_mod : grow;
+                const float4 r = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + gcol);
                 val.x += r.x; val.y += r.y; val.z += r.z; val.w += r.w;
               }
               if (p.out_kind == 1) {
@@ -317,7 +319,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
 
   GemmParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.split = g.split;
-  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr;
+  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.res_mod = g.res_mod;
   p.out = g.out; p.ldo = g.ldo; p.out_kind = g.out_kind; p.lo_off = g.lo_off; p.act = g.act;
   p.num_m_blocks = (g.M + BM - 1) / BM;
   p.num_n_blocks = g.N / BN;

@@ -1,0 +1,261 @@
+// Forward orchestration of the TimeSformer backbone on the resident token layout.
+//
+// Layout in HBM (all inside the caller-provided workspace):
+//   x    fp32 [M, 768]   residual stream.  Rows 0..M_t-1 are the patch tokens in (b, n, t) order (n-major, t-minor -
+//                        the reference's `b (n t) m`, models/timesformer.py:322) and rows M_t.. are the CLS rows
+//                        (one per clip; one per (clip, frame) for space_only), so every row-wise op (LayerNorm, the
+//                        qkv / proj / MLP GEMMs) covers patch and CLS tokens in ONE launch and no cat / repeat /
+//                        rearrange copy of the reference (:127-181) is ever materialised.
+//   a    bf16 [M, 768*k] GEMM A operand (LayerNorm output, im2col rows, attention output); k = 2 in split precision.
+//   qkv  bf16 [M, 2304*k]
+//   hid  bf16 [M, 3072*k] MLP hidden
+//   cls_acc fp32 [B, T, 768] per-frame CLS attention outputs (averaged over T before attn.proj, which is linear)
+//   emb  fp32 [N*T, 768] additive pos+time embedding table (periodic residual of the patch-embed GEMM)
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dvst.h"
+#include "dvst_internal.h"
+
+namespace dvst {
+
+namespace {
+constexpr int D = 768;
+constexpr float LN_EPS = 1e-6f;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+}  // namespace
+
+struct BlockW {
+  const float *tnorm_w = nullptr, *tnorm_b = nullptr, *norm1_w = nullptr, *norm1_b = nullptr, *norm2_w = nullptr,
+              *norm2_b = nullptr;
+  const void *tqkv_w = nullptr, *tproj_w = nullptr, *qkv_w = nullptr, *proj_w = nullptr, *fc1_w = nullptr,
+             *fc2_w = nullptr;
+  const float *tqkv_b = nullptr, *tproj_b = nullptr, *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr,
+              *fc2_b = nullptr;
+};
+
+struct Model {
+  dvst_config cfg;
+  std::unordered_map<std::string, const void*> named;
+  bool finalized = false;
+  const void* pe_w = nullptr;
+  const float *pe_b = nullptr, *cls_pos0 = nullptr, *pos = nullptr, *time_embed = nullptr, *norm_w = nullptr,
+              *norm_b = nullptr;
+  std::vector<BlockW> blocks;
+};
+
+struct Workspace {
+  float* x;
+  void* a;
+  void* qkv;
+  void* hid;
+  float* cls_acc;
+  float* emb;
+  float* tmp;  // [rows, 768] fp32 scratch for space_only's frame mean
+  size_t total;
+};
+
+static Workspace carve(const Model& m, void* base, long long B, int T, int gh, int gw) {
+  const long long N = static_cast<long long>(gh) * gw;
+  const long long n_cls = m.cfg.attention_type == DVST_ATTN_SPACE_ONLY ? B * T : B;
+  const long long M = B * N * T + n_cls;
+  const size_t k = m.cfg.precision == DVST_PRECISION_SPLIT ? 2 : 1;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = p ? p + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  Workspace w;
+  w.x = static_cast<float*>(take(static_cast<size_t>(M) * D * 4));
+  w.a = take(static_cast<size_t>(M) * D * 2 * k);
+  w.qkv = take(static_cast<size_t>(M) * 3 * D * 2 * k);
+  w.hid = take(static_cast<size_t>(M) * 4 * D * 2 * k);
+  w.cls_acc = static_cast<float*>(take(static_cast<size_t>(B) * T * D * 4));
+  w.emb = static_cast<float*>(take(static_cast<size_t>(N) * T * D * 4));
+  w.tmp = static_cast<float*>(take(m.cfg.attention_type == DVST_ATTN_SPACE_ONLY
+                                       ? static_cast<size_t>(B) * (N + 1) * D * 4 : 1024));
+  w.total = off;
+  return w;
+}
+
+}  // namespace dvst
+
+using namespace dvst;
+
+extern "C" {
+
+int dvst_create(const dvst_config* cfg, dvst_model** out) {
+  if (cfg == nullptr || out == nullptr) return set_error("dvst_create: null argument");
+  if (cfg->depth <= 0 || cfg->depth > 64) return set_error("dvst_create: bad depth %d", cfg->depth);
+  if (cfg->attention_type < 0 || cfg->attention_type > 2) return set_error("dvst_create: bad attention_type");
+  if (cfg->precision < 0 || cfg->precision > 1) return set_error("dvst_create: bad precision");
+  if (cfg->pos_grid <= 0 || cfg->num_frames <= 0) return set_error("dvst_create: bad pos_grid / num_frames");
+  Model* m = new Model();
+  m->cfg = *cfg;
+  *out = reinterpret_cast<dvst_model*>(m);
+  return 0;
+}
+
+void dvst_destroy(dvst_model* h) { delete reinterpret_cast<Model*>(h); }
+
+int dvst_set_weight(dvst_model* h, const char* name, const void* dev_ptr) {
+  if (h == nullptr || name == nullptr || dev_ptr == nullptr) return set_error("dvst_set_weight: null argument");
+  if (reinterpret_cast<uintptr_t>(dev_ptr) & 15) return set_error("dvst_set_weight(%s): pointer not 16-byte aligned", name);
+  Model* m = reinterpret_cast<Model*>(h);
+  m->named[name] = dev_ptr;
+  m->finalized = false;
+  return 0;
+}
+
+int dvst_finalize_weights(dvst_model* h) {
+  if (h == nullptr) return set_error("dvst_finalize_weights: null handle");
+  Model* m = reinterpret_cast<Model*>(h);
+  std::string missing;
+  auto get = [&](const std::string& k) -> const void* {
+    auto it = m->named.find(k);
+    if (it == m->named.end()) {
+      if (missing.size() < 300) missing += k + " ";
+      return nullptr;
+    }
+    return it->second;
+  };
+  auto getf = [&](const std::string& k) { return static_cast<const float*>(get(k)); };
+  const bool divided = m->cfg.attention_type == DVST_ATTN_DIVIDED;
+  m->pe_w = get("patch_embed.w");
+  m->pe_b = getf("patch_embed.b");
+  m->cls_pos0 = getf("cls_pos0");
+  m->pos = getf("pos_embed");
+  m->time_embed = m->cfg.attention_type == DVST_ATTN_SPACE_ONLY ? nullptr : getf("time_embed");
+  m->norm_w = getf("norm.w");
+  m->norm_b = getf("norm.b");
+  m->blocks.assign(m->cfg.depth, BlockW());
+  for (int i = 0; i < m->cfg.depth; ++i) {
+    const std::string p = "blocks." + std::to_string(i) + ".";
+    BlockW& b = m->blocks[i];
+    if (divided) {
+      b.tnorm_w = getf(p + "temporal_norm1.w"); b.tnorm_b = getf(p + "temporal_norm1.b");
+      b.tqkv_w = get(p + "temporal_attn.qkv.w"); b.tqkv_b = getf(p + "temporal_attn.qkv.b");
+      b.tproj_w = get(p + "temporal_projfc.w"); b.tproj_b = getf(p + "temporal_projfc.b");
+    }
+    b.norm1_w = getf(p + "norm1.w"); b.norm1_b = getf(p + "norm1.b");
+    b.qkv_w = get(p + "attn.qkv.w"); b.qkv_b = getf(p + "attn.qkv.b");
+    b.proj_w = get(p + "attn.proj.w"); b.proj_b = getf(p + "attn.proj.b");
+    b.norm2_w = getf(p + "norm2.w"); b.norm2_b = getf(p + "norm2.b");
+    b.fc1_w = get(p + "mlp.fc1.w"); b.fc1_b = getf(p + "mlp.fc1.b");
+    b.fc2_w = get(p + "mlp.fc2.w"); b.fc2_b = getf(p + "mlp.fc2.b");
+  }
+  if (!missing.empty()) return set_error("dvst_finalize_weights: missing tensors: %s", missing.c_str());
+  m->finalized = true;
+  return 0;
+}
+
+long long dvst_workspace_bytes(const dvst_model* h, int B, int T, int H, int W) {
+  if (h == nullptr || B <= 0 || T <= 0 || H < 16 || W < 16) return -1;
+  const Model* m = reinterpret_cast<const Model*>(h);
+  return static_cast<long long>(carve(*m, nullptr, B, T, H / 16, W / 16).total);
+}
+
+int dvst_forward_features(dvst_model* h, const float* x_in, int B, int T, int H, int W, float* out, int get_all,
+                          void* workspace, long long workspace_bytes, void* stream) {
+  if (h == nullptr) return set_error("dvst_forward_features: null handle");
+  Model* m = reinterpret_cast<Model*>(h);
+  if (!m->finalized) return set_error("dvst_forward_features: weights not finalized");
+  if (B <= 0 || T <= 0) return set_error("dvst_forward_features: bad batch %d / frames %d", B, T);
+  if (H % 16 || W % 16 || H < 16 || W < 16)
+    return set_error("dvst_forward_features: H, W must be multiples of the patch size 16 (got %dx%d)", H, W);
+  if ((reinterpret_cast<uintptr_t>(x_in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 1023))
+    return set_error("dvst_forward_features: x/out must be 16-byte and workspace 1024-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int gh = H / 16, gw = W / 16;
+  const long long N = static_cast<long long>(gh) * gw;
+  const int att = m->cfg.attention_type;
+  const long long n_cls = att == DVST_ATTN_SPACE_ONLY ? static_cast<long long>(B) * T : B;
+  const long long Mt = static_cast<long long>(B) * N * T;
+  const long long M = Mt + n_cls;
+  if (M > 2000000000LL / 2) return set_error("dvst_forward_features: too many rows (%lld)", M);
+  Workspace w = carve(*m, workspace, B, T, gh, gw);
+  if (static_cast<long long>(w.total) > workspace_bytes)
+    return set_error("dvst_forward_features: workspace too small (%lld < %lld)", workspace_bytes,
+                     static_cast<long long>(w.total));
+  const int split = m->cfg.precision == DVST_PRECISION_SPLIT ? 1 : 0;
+  const int act_kind = split ? 2 : 0;            // bf16 or bf16 hi/lo
+  const long long lda = split ? 2 * D : D;       // row stride of `a`
+  const long long ldq = split ? 6 * D : 3 * D;   // row stride of `qkv`
+  const long long ldh = split ? 8 * D : 4 * D;   // row stride of `hid`
+  int rc;
+#define DVST_TRY(expr) do { if ((rc = (expr)) != 0) return rc; } while (0)
+
+  auto gemm = [&](const void* A, long long lda_, const void* Wt, const float* bias, long long rows, int Nn, int K,
+                  const float* residual, long long res_mod, void* o, long long ldo, int out_kind, int act) {
+    GemmArgs g;
+    g.A = A; g.lda = lda_; g.W = Wt; g.ldw = split ? 2LL * K : K; g.bias = bias;
+    g.M = static_cast<int>(rows); g.N = Nn; g.K = K; g.split = split;
+    g.residual = residual; g.ldr = D; g.res_mod = res_mod;
+    g.out = o; g.ldo = ldo; g.out_kind = out_kind; g.lo_off = ldo / 2; g.act = act;
+    return launch_gemm(g, st);
+  };
+  auto ln = [&](const float* src, const float* gw_, const float* gb_, long long rows) {
+    return launch_layernorm768(src, D, gw_, gb_, w.a, lda, act_kind, D, rows, LN_EPS, st);
+  };
+
+  // ---- patch embedding + positional / temporal embedding (timesformer.py:203-209,287-323) ----
+  DVST_TRY(launch_embed_table(m->pos, m->cfg.pos_grid, m->time_embed, m->cfg.num_frames, w.emb, gh, gw, T, st));
+  DVST_TRY(launch_im2col16(x_in, w.a, lda, split, D, B, T, H, W, st));
+  DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.emb, N * T, w.x, D, 1, 0));
+  DVST_TRY(launch_broadcast_row768(m->cls_pos0, w.x + Mt * D, D, static_cast<int>(n_cls), st));
+
+  for (int i = 0; i < m->cfg.depth; ++i) {
+    const BlockW& b = m->blocks[i];
+    if (att == DVST_ATTN_DIVIDED) {
+      // temporal attention over the T tokens of every (b, n); CLS rows excluded (:127-135)
+      DVST_TRY(ln(w.x, b.tnorm_w, b.tnorm_b, Mt));
+      DVST_TRY(gemm(w.a, lda, b.tqkv_w, b.tqkv_b, Mt, 3 * D, D, nullptr, 0, w.qkv, ldq, act_kind, 0));
+      DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, nullptr, 0, B, T, static_cast<int>(N), Mt, split, st));
+      // temporal_fc(proj(.)) folded into one 768x768 GEMM at pack time; residual add fused (:131-135)
+      DVST_TRY(gemm(w.a, lda, b.tproj_w, b.tproj_b, Mt, D, D, w.x, 0, w.x, D, 1, 0));
+    }
+    // spatial (or joint / per-frame) attention (:120-123,140-181)
+    DVST_TRY(ln(w.x, b.norm1_w, b.norm1_b, M));
+    DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, 0, w.qkv, ldq, act_kind, 0));
+    const int mode = att == DVST_ATTN_DIVIDED ? 1 : (att == DVST_ATTN_JOINT ? 2 : 3);
+    DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, w.cls_acc, mode, B, T, static_cast<int>(N), Mt, split, st));
+    if (att == DVST_ATTN_DIVIDED)
+      DVST_TRY(launch_cls_mean(w.cls_acc, static_cast<__nv_bfloat16*>(w.a) + Mt * lda, lda, split, D, B, T, nullptr, st));
+    DVST_TRY(gemm(w.a, lda, b.proj_w, b.proj_b, M, D, D, w.x, 0, w.x, D, 1, 0));
+    // MLP (:184)
+    DVST_TRY(ln(w.x, b.norm2_w, b.norm2_b, M));
+    DVST_TRY(gemm(w.a, lda, b.fc1_w, b.fc1_b, M, 4 * D, D, nullptr, 0, w.hid, ldh, act_kind, 1));
+    DVST_TRY(gemm(w.hid, ldh, b.fc2_w, b.fc2_b, M, D, 4 * D, w.x, 0, w.x, D, 1, 0));
+  }
+
+  // ---- final norm (:338-345) ----
+  if (att == DVST_ATTN_SPACE_ONLY) {
+    // frame average of every token, then LayerNorm
+    if (get_all) {
+      DVST_TRY(launch_cls_mean(w.x, nullptr, 0, 0, 0, static_cast<long long>(B) * N, T, w.tmp + static_cast<long long>(B) * D, st));
+      DVST_TRY(launch_cls_mean(w.x + Mt * D, nullptr, 0, 0, 0, B, T, w.tmp, st));
+      DVST_TRY(launch_layernorm768(w.tmp, D, m->norm_w, m->norm_b, out, D, 1, 0, B, LN_EPS, st, 1, N + 1, 0));
+      DVST_TRY(launch_layernorm768(w.tmp + static_cast<long long>(B) * D, D, m->norm_w, m->norm_b, out, D, 1, 0,
+                                   static_cast<long long>(B) * N, LN_EPS, st, N, N + 1, 1));
+    } else {
+      DVST_TRY(launch_cls_mean(w.x + Mt * D, nullptr, 0, 0, 0, B, T, w.tmp, st));
+      DVST_TRY(launch_layernorm768(w.tmp, D, m->norm_w, m->norm_b, out, D, 1, 0, B, LN_EPS, st));
+    }
+  } else if (get_all) {
+    // reference order: [B, 1 + N*T, 768], CLS first
+    DVST_TRY(launch_layernorm768(w.x + Mt * D, D, m->norm_w, m->norm_b, out, D, 1, 0, B, LN_EPS, st, 1, N * T + 1, 0));
+    DVST_TRY(launch_layernorm768(w.x, D, m->norm_w, m->norm_b, out, D, 1, 0, Mt, LN_EPS, st, N * T, N * T + 1, 1));
+  } else {
+    // only the CLS rows are needed: LayerNorm is row-wise, so this equals norm(x)[:, 0] (:342-345)
+    DVST_TRY(launch_layernorm768(w.x + Mt * D, D, m->norm_w, m->norm_b, out, D, 1, 0, B, LN_EPS, st));
+  }
+#undef DVST_TRY
+  return 0;
+}
+
+}  // extern "C"

@@ -1,8 +1,13 @@
-/* libdvst.so - C ABI of the B200-native scoring path (TimeSformer forward + DINO head/loss).
+/* libdvst.so - C ABI of the B200-native scoring path (TimeSformer forward + DINO head / loss).
+ *
+ * The reference (Luke-537/Dino-Video-Summarization-Transformer) is pure Python: its boundary for this path is the
+ * nn.Module level.  This header is the FFI the Python host side (dvst_b200/*.py, ctypes) binds;
+ * each entry point cites the reference interface it stands in for.
  *
  * Conventions: every function returns 0 on success, DVST_ERR otherwise (message via dvst_last_error(), thread
- * local); nothing throws.  All data pointers are caller-owned DEVICE pointers unless stated otherwise; `stream` is a
- * cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).  No call synchronises the device.
+ * local); nothing throws.  All data pointers are caller-owned DEVICE pointers (tensor.data_ptr()) unless stated
+ * otherwise; `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).  No call
+ * synchronises the device or allocates device memory.  A model handle is not re-entrant (one per process / GPU).
  */
 #ifndef DVST_H_
 #define DVST_H_
@@ -14,11 +19,60 @@ extern "C" {
 #define DVST_ABI_VERSION 1
 #define DVST_ERR 1
 
+/* attention_type: cfg.TIMESFORMER.ATTENTION_TYPE (models/timesformer.py:97,120-124) */
+#define DVST_ATTN_DIVIDED 0
+#define DVST_ATTN_JOINT 1
+#define DVST_ATTN_SPACE_ONLY 2
+/* precision: 0 = bf16 operands / fp32 accumulate; 1 = 2-term bf16 split (hi*hi + hi*lo + lo*hi), ~16 mantissa bits */
+#define DVST_PRECISION_BF16 0
+#define DVST_PRECISION_SPLIT 1
+
+typedef struct dvst_config {
+  int depth;          /* number of blocks (12 for ViT-B, models/timesformer.py:595) */
+  int num_frames;     /* cfg.DATA.NUM_FRAMES = rows of time_embed (:234) */
+  int pos_grid;       /* sqrt(#patch positions of pos_embed) = cfg.DATA.TRAIN_CROP_SIZE / 16 (:231) */
+  int attention_type; /* DVST_ATTN_* */
+  int precision;      /* DVST_PRECISION_* */
+} dvst_config;
+
+typedef struct dvst_model dvst_model; /* opaque */
+
 const char* dvst_last_error(void);
 /* Number of kernel launches issued by the library so far (bench.py's `gpu_launches`). */
 long long dvst_launch_count(void);
 int dvst_abi_version(void);
 
+/* ---- model handle: replaces VisionTransformer.__init__/load_state_dict (models/timesformer.py:212-263) ----------- */
+int dvst_create(const dvst_config* cfg, dvst_model** out);
+void dvst_destroy(dvst_model* m);
+/* Registers one PACKED tensor (device pointer, must stay alive while the handle is used).  Names:
+ *   patch_embed.w  bf16 [768, 768*k] (conv weight flattened (c,ky,kx); k = 2 in split precision: [hi | lo])
+ *   patch_embed.b, cls_pos0 (= cls_token + pos_embed[0]), norm.w, norm.b          fp32 [768]
+ *   pos_embed fp32 [1 + pos_grid^2, 768], time_embed fp32 [num_frames, 768]
+ *   blocks.<i>.{temporal_norm1,norm1,norm2}.{w,b}                                   fp32 [768]
+ *   blocks.<i>.{temporal_attn.qkv,attn.qkv}.w bf16 [2304, 768*k], .b fp32 [2304]
+ *   blocks.<i>.temporal_projfc.w bf16 [768, 768*k] = temporal_fc.weight @ temporal_attn.proj.weight, .b fp32 [768]
+ *   blocks.<i>.attn.proj.{w,b}, blocks.<i>.mlp.fc1.{w [3072,768*k], b}, blocks.<i>.mlp.fc2.{w [768,3072*k], b}    */
+int dvst_set_weight(dvst_model* m, const char* name, const void* dev_ptr);
+int dvst_finalize_weights(dvst_model* m);
+
+/* Scratch bytes dvst_forward_features needs for a [B,3,T,H,W] batch (-1 on bad arguments). */
+long long dvst_workspace_bytes(const dvst_model* m, int B, int T, int H, int W);
+
+/* VisionTransformer.forward(x, use_head=False) / forward_features(x, get_all) - models/timesformer.py:285-351.
+ *   x   fp32 [B,3,T,H,W] (NCTHW, H and W multiples of 16)
+ *   out fp32 [B,768] (get_all = 0: LayerNorm'ed CLS feature) or [B, 1+N*T, 768] (get_all = 1, reference token order;
+ *       [B, 1+N, 768] for space_only) */
+int dvst_forward_features(dvst_model* m, const float* x, int B, int T, int H, int W, float* out, int get_all,
+                          void* workspace, long long workspace_bytes, void* stream);
+
+/* Scoring DINOLoss.forward for `pairs` rows at once - dino_similarity.py:129-135:
+ *   loss[p] = sum_j -softmax((t[p]-center)/teacher_temp)_j * log_softmax(s[p]/student_temp)_j
+ * student / teacher fp32 [pairs, dim] (row strides lds / ldt), center fp32 [dim] or NULL (zeros), loss fp32 [pairs]. */
+int dvst_pair_loss(const float* student, long long lds, const float* teacher, long long ldt, const float* center,
+                   float teacher_temp, float student_temp, int dim, int pairs, float* loss, void* stream);
+
+/* ---- building blocks (exported for unit tests and the DINO head) -------------------------------------------------- */
 /* out[M,N] = epilogue(A[M,K] x W[N,K]^T).  bf16 operands, fp32 accumulate (tcgen05 / TMEM).
  * Replaces torch.nn.Linear as used by models/timesformer.py:41-52,63-64,71,83,108,133 and
  * vision_transformer.py:254-266.
@@ -28,6 +82,14 @@ int dvst_abi_version(void);
 int dvst_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
                    int split, const float* residual, long long ldr, void* out, long long ldo, int out_kind,
                    long long lo_off, int act, void* stream);
+/* nn.LayerNorm(768, eps) over M rows of fp32 (models/timesformer.py:99,105,112,245).  out_kind as above. */
+int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,
+                      int out_kind, long long lo_off, long long M, float eps, void* stream);
+/* Attention.forward minus the linears (models/timesformer.py:77-81) on the packed qkv rows [*, ld] bf16.
+ *   mode 0 temporal, 1 spatial (shared CLS row per clip, CLS outputs -> cls_out fp32 [B,T,768]), 2 joint,
+ *   3 space-only; cls_base = index of the first CLS row; out bf16 [*, ldo]. */
+int dvst_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                   int N, long long cls_base, void* stream);
 
 #ifdef __cplusplus
 }

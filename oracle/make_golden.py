@@ -1,0 +1,219 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (imported from /root/reference via ref_shim).
+
+TEST INFRASTRUCTURE ONLY; runs in the authoring container (the reference does not travel to the GPU box).
+    python oracle/make_golden.py            # ~2-3 minutes on 8 cores
+
+Inputs and weights are NOT stored: they are regenerated bit-identically from seeds by dvst_b200.testing (CPU
+torch.Generator).  Stored: the reference's fp32-CPU outputs for those inputs.
+"""
+import functools
+import json
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import dvst_b200  # noqa: E402,F401
+from dvst_b200.testing import (synth_backbone_state_dict, synth_clips, synth_head_state_dict,  # noqa: E402
+                               synth_video)
+import ref_shim  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+os.makedirs(GOLD, exist_ok=True)
+R = ref_shim.load()
+torch.set_num_threads(os.cpu_count())
+
+
+def ref_backbone(sd, depth, num_frames, img_size, attention_type):
+    m = R["VisionTransformer"](img_size=img_size, num_classes=0, patch_size=16, embed_dim=768, depth=depth,
+                               num_heads=12, mlp_ratio=4, qkv_bias=True,
+                               norm_layer=functools.partial(torch.nn.LayerNorm, eps=1e-6), num_frames=num_frames,
+                               attention_type=attention_type)
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+# Backbone cases: (name, seed_w, depth, T0, attention, seed_x, B, T, crop).  img_size (pos_embed grid) is always 224.
+BACKBONE_CASES = [
+    ("cfg1_full_T8", 0, 12, 8, "divided_space_time", 100, 2, 8, 224),
+    ("full_T3", 0, 12, 8, "divided_space_time", 101, 2, 3, 224),
+    ("d2_T5", 1, 2, 8, "divided_space_time", 102, 3, 5, 224),
+    ("d2_T30", 1, 2, 8, "divided_space_time", 103, 1, 30, 224),
+    ("d2_T16", 1, 2, 8, "divided_space_time", 104, 2, 16, 224),
+    ("d2_T4_crop96", 1, 2, 8, "divided_space_time", 105, 2, 4, 96),
+    ("d2_T1", 1, 2, 8, "divided_space_time", 106, 2, 1, 224),
+    ("d2_joint_T4", 2, 2, 8, "joint_space_time", 107, 2, 4, 224),
+    ("d2_space_T4", 3, 2, 8, "space_only", 108, 2, 4, 224),
+]
+
+
+def gen_backbone():
+    out = {}
+    cache = {}
+    for (name, sw, depth, T0, att, sx, B, T, crop) in BACKBONE_CASES:
+        key = (sw, depth, T0, att)
+        if key not in cache:
+            sd = synth_backbone_state_dict(sw, depth=depth, num_frames=T0, attention_type=att)
+            cache[key] = ref_backbone(sd, depth, T0, 224, att)
+        m = cache[key]
+        x = synth_clips(sx, B, T, crop, crop)
+        with torch.no_grad():
+            feat = m(x)
+        out[name] = dict(seed_w=sw, depth=depth, num_frames=T0, attention_type=att, seed_x=sx, B=B, T=T, crop=crop,
+                         feat=feat.clone())
+        print("backbone", name, tuple(feat.shape), float(feat.std()))
+    torch.save(out, os.path.join(GOLD, "backbone.pt"))
+    return cache
+
+
+def gen_head_loss(models):
+    """DINOHead logits summary + scoring losses (mode R and mode H) + training loss / center update."""
+    out = {}
+    m = models[(0, 12, 8, "divided_space_time")]
+    xs = synth_clips(200, 4, 3)   # 4 student clips, T=3
+    xt = synth_clips(201, 4, 8)   # 4 teacher clips, T=8  (BASELINE config 1: 4 candidate subsets)
+    with torch.no_grad():
+        fs, ft = m(xs), m(xt)
+    lossR = R["DINOLoss"](out_dim=768, teacher_temp=0.02, student_temp=0.3)
+    out["feat_s"], out["feat_t"] = fs.clone(), ft.clone()
+    out["loss_R"] = torch.stack([lossR(fs[k], ft[k]) for k in range(4)]).clone()
+    for out_dim in (65536, 4096):
+        hsd = synth_head_state_dict(2, out_dim=out_dim)
+        head = R["DINOHead"](768, out_dim)
+        head.load_state_dict(hsd, strict=True)
+        head.eval()
+        with torch.no_grad():
+            ls, lt = head(fs), head(ft)
+        g = torch.Generator().manual_seed(7)
+        center = torch.randn(1, out_dim, generator=g) * 0.05
+        for (tt, st, cname, c) in [(0.04, 0.1, "zero", torch.zeros(1, out_dim)), (0.04, 0.1, "rand", center),
+                                   (0.02, 0.3, "zero", torch.zeros(1, out_dim)), (0.07, 0.1, "rand", center)]:
+            L = R["DINOLoss"](out_dim=out_dim, teacher_temp=tt, student_temp=st)
+            L.center.copy_(c)
+            with torch.no_grad():
+                out[f"loss_H{out_dim}_{tt}_{st}_{cname}"] = torch.stack([L(ls[k], lt[k]) for k in range(4)]).clone()
+        out[f"logits_s_{out_dim}_head8"] = ls[:, :8].clone()
+        out[f"logits_s_{out_dim}_sum"] = ls.sum(dim=1).clone()
+        out[f"logits_t_{out_dim}_colsum_head8"] = lt.sum(dim=0)[:8].clone()
+        out[f"center_seed7_{out_dim}_head8"] = center[0, :8].clone()
+    torch.save(out, os.path.join(GOLD, "head_loss.pt"))
+    print("head/loss", {k: (v.tolist() if v.numel() <= 4 else tuple(v.shape)) for k, v in out.items()})
+
+
+def gen_windows():
+    """(j, l) window starts from the reference's own view builder, frames tagged by index."""
+    gv = R["dino_loss_loader"].get_views_of_video_same_size
+    out = {}
+    for F in list(range(3, 75)) + [100, 300, 450]:
+        frames = torch.arange(F, dtype=torch.float32).reshape(F, 1, 1, 1).expand(F, 3, 1, 1).contiguous()
+        views = gv(frames, 3, 30)  # [2F,3,G,1,1]
+        G = views.shape[2]
+        starts = []
+        for i in range(F):
+            loc, glob = views[2 * i], views[2 * i + 1]
+            starts.append((int(loc[0, 0, 0, 0]), int(glob[0, 0, 0, 0])))
+            assert int(loc[0, 2, 0, 0]) == starts[-1][0] + 2 and int(glob[0, G - 1, 0, 0]) == starts[-1][1] + G - 1
+        out[str(F)] = dict(G=G, starts=starts)
+    json.dump(out, open(os.path.join(GOLD, "windows.json"), "w"))
+    print("windows", len(out))
+
+
+def gen_selection():
+    """Index lists from the reference FrameSelectionLoader (adaptive, return_type='Indices') on (a) 48 videos of the
+    shipped MSVD loss file and (b) 96 synthetic loss lists; read_video is mocked to give the right frame count."""
+    import importlib
+    fsl = importlib.import_module("datasets_custom.frame_selection_loader")
+    shipped = json.load(open(os.path.join(ref_shim.REF_ROOT, "loss_values", "loss_msvd_4_3_30.json")))
+    rng = np.random.RandomState(0)
+    keys = sorted(shipped.keys())
+    pick = [keys[i] for i in rng.choice(len(keys), 48, replace=False)]
+    cases = {}
+    for k in pick:
+        cases[k] = dict(loss=shipped[k], n_unsampled=4 * len(shipped[k]) - int(rng.randint(0, 4)))
+    for i in range(96):
+        F = int(rng.randint(3, 120))
+        loss = (rng.gamma(1.5, 2.0, size=F) + (rng.rand(F) < 0.1) * 8.0).astype(np.float32).astype(np.float64)
+        if i % 7 == 0:
+            loss[:] = loss[0]  # constant curve (dummy videos)
+        if i % 11 == 0:
+            loss[: F // 2] = 1e-6  # mass concentrated at the end: forces the de-duplication walk
+        cases[f"synth{i:03d}"] = dict(loss=loss.tolist(), n_unsampled=4 * F - int(rng.randint(0, 4)))
+    with tempfile.TemporaryDirectory() as td:
+        json.dump({k: v["loss"] for k, v in cases.items()}, open(os.path.join(td, "loss.json"), "w"))
+        names = list(cases.keys())
+        with open(os.path.join(td, "test.csv"), "w") as f:
+            for n in names:
+                f.write(f"{n}.avi 0\n")
+        cfg = types.SimpleNamespace(
+            TEST=types.SimpleNamespace(NUM_ENSEMBLE_VIEWS=1), LOSS_FILE=os.path.join(td, "loss.json"), DATASET="MSVD",
+            DATA=types.SimpleNamespace(PATH_TO_DATA_DIR=td, PATH_PREFIX=td, PATH_LABEL_SEPARATOR=" ",
+                                       MEAN=[0.45] * 3, STD=[0.225] * 3))
+        cur = {}
+        fsl.io.read_video = lambda path, pts_unit="sec": (
+            torch.zeros(cases[os.path.splitext(os.path.basename(path))[0]]["n_unsampled"], 2, 2, 3,
+                        dtype=torch.uint8), None, None)
+        for N in (8, 16):
+            ds = fsl.FrameSelectionLoader(cfg, 4, "adaptive", N, False, "Indices", "test")
+            for i, n in enumerate(names):
+                idx, _, fname = ds[i]
+                cases[n][f"idx{N}"] = [int(v) for v in idx]
+    json.dump(cases, open(os.path.join(GOLD, "selection.json"), "w"))
+    print("selection", len(cases))
+
+
+def gen_driver(models):
+    """Run the reference's own dino_similarity() loop (loader -> views -> model -> DINOLoss -> export_loss JSON) on two
+    tiny synthetic videos with read_video / torch.load / .cuda mocked."""
+    ds = R["dino_similarity"]
+    dll = R["dino_loss_loader"]
+    sd = synth_backbone_state_dict(0, depth=12, num_frames=8)
+    vids = {"vidA": 24, "vidB": 13}  # unsampled frame counts -> F = 6 and 4 sampled frames at rate 4
+    raw = {}
+    for i, (k, n) in enumerate(vids.items()):
+        g = torch.Generator().manual_seed(300 + i)
+        raw[k] = torch.randint(0, 256, (n, 224, 224, 3), generator=g, dtype=torch.uint8)
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "test.csv"), "w") as f:
+            for k in vids:
+                f.write(f"{k}.avi 0\n")
+        outp = os.path.join(td, "loss.json")
+        args = types.SimpleNamespace(
+            pretrained_weights="synthetic", num_workers=0, batch_size_per_gpu=8,
+            TEST=types.SimpleNamespace(NUM_ENSEMBLE_VIEWS=1),
+            DATA=types.SimpleNamespace(PATH_TO_DATA_DIR=td, PATH_PREFIX=td, PATH_LABEL_SEPARATOR=" ",
+                                       MEAN=[0.45] * 3, STD=[0.225] * 3, TRAIN_CROP_SIZE=224, NUM_FRAMES=8),
+            MODEL=types.SimpleNamespace(NUM_CLASSES=400),
+            TIMESFORMER=types.SimpleNamespace(ATTENTION_TYPE="divided_space_time", PRETRAINED_MODEL=""))
+        dll.io.read_video = lambda path, pts_unit="sec": (
+            raw[os.path.splitext(os.path.basename(path))[0]], None, None)
+        orig_load, orig_tcuda, orig_mcuda = ds.torch.load, torch.Tensor.cuda, torch.nn.Module.cuda
+        ds.torch.load = lambda *a, **k: {"backbone." + k_: v for k_, v in sd.items()}
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        try:
+            ds.dino_similarity(args, 3, 30, 4, outp)
+        finally:
+            ds.torch.load, torch.Tensor.cuda, torch.nn.Module.cuda = orig_load, orig_tcuda, orig_mcuda
+        result = json.load(open(outp))
+    json.dump(dict(seed_w=0, videos={k: dict(n_unsampled=n, seed=300 + i) for i, (k, n) in enumerate(vids.items())},
+                   loss=result), open(os.path.join(GOLD, "driver_loss.json"), "w"))
+    print("driver", result)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["backbone", "head", "windows", "selection", "driver"]
+    models = gen_backbone() if ("backbone" in what or "head" in what) else None
+    if "head" in what:
+        gen_head_loss(models)
+    if "windows" in what:
+        gen_windows()
+    if "selection" in what:
+        gen_selection()
+    if "driver" in what:
+        gen_driver(models)
