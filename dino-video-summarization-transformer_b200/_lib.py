@@ -36,6 +36,17 @@ SIGNATURES = {
                                       c_void_p]),
     "dvst_pair_loss": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_float, c_float, c_int, c_int, c_void_p,
                                c_void_p]),
+    "dvst_forward_windows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_ll, c_void_p]),
+    "dvst_pair_loss_indexed": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_float, c_float,
+                                       c_int, c_int, c_void_p, c_void_p]),
+    "dvst_head_loss_scratch_bytes": (c_ll, [c_int]),
+    "dvst_head_loss": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_void_p,
+                               c_void_p, c_ll, c_void_p]),
+    "dvst_colsum": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p]),
+    "dvst_center_ema": (c_int, [c_void_p, c_void_p, c_float, c_float, c_int, c_void_p]),
+    "dvst_cast_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_ll, c_ll, c_int, c_void_p]),
+    "dvst_l2norm_rows": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p]),
     "dvst_layernorm768": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_float,
                                   c_void_p]),
     "dvst_attention": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p]),

@@ -45,8 +45,49 @@ int dvst_pair_loss(const float* student, long long lds, const float* teacher, lo
                    float teacher_temp, float student_temp, int dim, int pairs, float* loss, void* stream) {
   if (dim <= 0 || pairs < 0) return set_error("dvst_pair_loss: bad dim %d / pairs %d", dim, pairs);
   if (teacher_temp <= 0.f || student_temp <= 0.f) return set_error("dvst_pair_loss: temperatures must be > 0");
-  return launch_pair_loss(student, lds, teacher, ldt, center, teacher_temp, student_temp, dim, pairs, loss,
-                          static_cast<cudaStream_t>(stream));
+  return launch_pair_loss(student, lds, teacher, ldt, center, teacher_temp, student_temp, dim, pairs, loss, nullptr,
+                          nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_pair_loss_indexed(const float* student, long long lds, const int* s_idx, const float* teacher, long long ldt,
+                           const int* t_idx, const float* center, float teacher_temp, float student_temp, int dim,
+                           int pairs, float* loss, void* stream) {
+  if (dim <= 0 || pairs < 0) return set_error("dvst_pair_loss_indexed: bad dim %d / pairs %d", dim, pairs);
+  if (teacher_temp <= 0.f || student_temp <= 0.f) return set_error("dvst_pair_loss_indexed: temperatures must be > 0");
+  return launch_pair_loss(student, lds, teacher, ldt, center, teacher_temp, student_temp, dim, pairs, loss, s_idx,
+                          t_idx, static_cast<cudaStream_t>(stream));
+}
+
+long long dvst_head_loss_scratch_bytes(int pairs) { return pairs > 0 ? head_loss_scratch_bytes(pairs) : 0; }
+
+int dvst_head_loss(const void* zs, const void* zt, long long ldz, const void* w, const float* center,
+                   float teacher_temp, float student_temp, int pairs, int out_dim, float* loss, void* scratch,
+                   long long scratch_bytes, void* stream) {
+  if (teacher_temp <= 0.f || student_temp <= 0.f) return set_error("dvst_head_loss: temperatures must be > 0");
+  if ((reinterpret_cast<uintptr_t>(zs) & 15) || (reinterpret_cast<uintptr_t>(zt) & 15) ||
+      (reinterpret_cast<uintptr_t>(w) & 15) || (ldz % 8))
+    return set_error("dvst_head_loss: operands must be 16-byte aligned, ldz a multiple of 8");
+  return launch_head_loss(zs, zt, ldz, w, center, teacher_temp, student_temp, pairs, out_dim, loss, scratch,
+                          scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_cast_bf16(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off, long long M,
+                   int cols, void* stream) {
+  return launch_cast_bf16(in, ldi, out, ldo, split, lo_off, M, cols, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_l2norm_rows(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off,
+                     float* out_f32, long long M, int cols, void* stream) {
+  return launch_l2norm_rows(in, ldi, out, ldo, split, lo_off, out_f32, M, cols, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_colsum(const float* in, long long ldi, float* out, int rows, int cols, void* stream) {
+  return launch_colsum(in, ldi, out, rows, cols, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_center_ema(float* center, const float* batch_sum, float denom, float momentum, int cols, void* stream) {
+  if (denom <= 0.f) return set_error("dvst_center_ema: denom must be > 0");
+  return launch_center_ema(center, batch_sum, denom, momentum, cols, static_cast<cudaStream_t>(stream));
 }
 
 int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,

@@ -36,17 +36,28 @@ int launch_layernorm768(const float* x, long long ldx, const float* gamma, const
                         long long ldo, int out_kind, long long lo_off, long long M, float eps, cudaStream_t st,
                         long long rm_group = 0, long long rm_stride = 0, long long rm_offset = 0);
 int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,
-                    cudaStream_t st);
+                    const int* starts, cudaStream_t st);
+int launch_cast_bf16(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off, long long M,
+                     int cols, cudaStream_t st);
+int launch_l2norm_rows(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off,
+                       float* out_f32, long long M, int cols, cudaStream_t st);
+int launch_colsum(const float* in, long long ldi, float* out, int rows, int cols, cudaStream_t st);
+int launch_center_ema(float* center, const float* batch_sum, float denom, float momentum, int cols, cudaStream_t st);
 int launch_broadcast_row768(const float* src, float* dst, long long ldd, int nrows, cudaStream_t st);
 int launch_cls_mean(const float* in, void* out, long long ldo, int split, long long lo_off, long long B, int T,
                     float* out_f32, cudaStream_t st);
 int launch_pair_loss(const float* s, long long lds, const float* t, long long ldt, const float* center, float tt,
-                     float ts, int dim, int pairs, float* loss, cudaStream_t st);
+                     float ts, int dim, int pairs, float* loss, const int* s_idx, const int* t_idx, cudaStream_t st);
 int launch_embed_table(const float* pos, int P, const float* time_embed, int T0, float* out, int gh, int gw, int T,
                        cudaStream_t st);
 // mode: 0 temporal, 1 spatial (shared CLS per clip), 2 joint, 3 space-only (one CLS row per (b, t))
 int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                      int N, long long cls_base, int split, cudaStream_t st);
+
+long long head_loss_scratch_bytes(int P);
+int launch_head_loss(const void* zs, const void* zt, long long ldz, const void* w, const float* center, float tt,
+                     float ts, int P, int out_dim, float* loss, void* scratch, long long scratch_bytes,
+                     cudaStream_t st);
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols);

@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restri
 // One thread moves 8 consecutive kx (two float4 loads, one 16-byte bf16 store).
 __global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                        long long ldo, int split, long long lo_off, int B, int T,
-                                                       int H, int W, int gh, int gw) {
+                                                       int H, int W, int gh, int gw,
+                                                       const int* __restrict__ starts) {
   const long long total = static_cast<long long>(B) * gh * gw * T * 96;  // 96 chunks of 8 per row
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -97,8 +98,11 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__
   const int b = static_cast<int>(bn / (gh * gw));
   const int c = chunk / 32, rem = chunk % 32, ky = rem / 2, kx0 = (rem % 2) * 8;
   const int py = n / gw, px = n % gw;
-  const float* src =
-      x + (((static_cast<long long>(b) * 3 + c) * T + t) * H + (py * 16 + ky)) * W + px * 16 + kx0;
+  // starts == null: x is a clip batch [B,3,T,H,W]; else x is a frame-major video [F,3,H,W] and clip b is the
+  // window of T consecutive frames beginning at starts[b] (device-side view construction, dino_loss_loader.py:126-171)
+  const float* src = starts == nullptr
+      ? x + (((static_cast<long long>(b) * 3 + c) * T + t) * H + (py * 16 + ky)) * W + px * 16 + kx0
+      : x + ((static_cast<long long>(__ldg(starts + b) + t) * 3 + c) * H + (py * 16 + ky)) * W + px * 16 + kx0;
   const float4 a0 = __ldg(reinterpret_cast<const float4*>(src));
   const float4 a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
   __nv_bfloat16* o = out + row * ldo + chunk * 8;
@@ -170,12 +174,14 @@ __global__ void cls_mean_kernel(const float* __restrict__ in, __nv_bfloat16* __r
 __global__ void __launch_bounds__(128) pair_loss_kernel(const float* __restrict__ s, long long lds,
                                                         const float* __restrict__ t, long long ldt,
                                                         const float* __restrict__ center, float inv_tt, float inv_ts,
-                                                        int dim, int pairs, float* __restrict__ loss) {
+                                                        int dim, int pairs, float* __restrict__ loss,
+                                                        const int* __restrict__ s_idx,
+                                                        const int* __restrict__ t_idx) {
   const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (p >= pairs) return;
   const int lane = threadIdx.x & 31;
-  const float* sr = s + p * lds;
-  const float* tr = t + p * ldt;
+  const float* sr = s + static_cast<long long>(s_idx ? s_idx[p] : p) * lds;
+  const float* tr = t + static_cast<long long>(t_idx ? t_idx[p] : p) * ldt;
   float ms = -INFINITY, mt = -INFINITY;
   for (int j = lane; j < dim; j += 32) {
     ms = fmaxf(ms, sr[j] * inv_ts);
@@ -197,7 +203,91 @@ __global__ void __launch_bounds__(128) pair_loss_kernel(const float* __restrict_
   if (lane == 0) loss[p] = (ms + logf(zs)) - cross / zt;
 }
 
+// fp32 [M, cols] -> bf16 (+ lo)
+__global__ void cast_bf16_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out,
+                                 long long ldo, int split, long long lo_off, long long M, int cols) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= M * cols) return;
+  const long long r = idx / cols;
+  const int c = static_cast<int>(idx % cols);
+  const float v = in[r * ldi + c];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  out[r * ldo + c] = h;
+  if (split) out[r * ldo + lo_off + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// F.normalize(x, dim=-1, p=2) (eps 1e-12) over rows of `cols` fp32 (vision_transformer.py:280), bf16 (+ lo) output;
+// optionally also the fp32 normalised rows.  One warp per row.
+__global__ void __launch_bounds__(128) l2norm_rows_kernel(const float* __restrict__ in, long long ldi,
+                                                          __nv_bfloat16* __restrict__ out, long long ldo, int split,
+                                                          long long lo_off, float* __restrict__ out_f32, long long M,
+                                                          int cols) {
+  const long long r = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const int lane = threadIdx.x & 31;
+  float ss = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float v = in[r * ldi + c]; ss += v * v; }
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  for (int c = lane; c < cols; c += 32) {
+    const float v = in[r * ldi + c] * inv;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[r * ldo + c] = h;
+    if (split) out[r * ldo + lo_off + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (out_f32) out_f32[r * cols + c] = v;
+  }
+}
+
+// out[c] = sum_r in[r, c]   (batch_center = torch.sum(teacher_output, dim=0), train_ssl.py:686)
+__global__ void colsum_kernel(const float* __restrict__ in, long long ldi, float* __restrict__ out, int rows, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += in[static_cast<long long>(r) * ldi + c];
+  out[c] = s;
+}
+
+// center = center * momentum + (batch_sum / denom) * (1 - momentum)   (train_ssl.py:688-691)
+__global__ void center_ema_kernel(float* __restrict__ center, const float* __restrict__ batch_sum, float inv_denom,
+                                  float momentum, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  center[c] = center[c] * momentum + batch_sum[c] * inv_denom * (1.0f - momentum);
+}
+
 }  // namespace
+
+int launch_cast_bf16(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off, long long M,
+                     int cols, cudaStream_t st) {
+  if (M <= 0) return 0;
+  const long long total = M * cols;
+  cast_bf16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      in, ldi, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, M, cols);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("cast launch failed");
+}
+
+int launch_l2norm_rows(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off,
+                       float* out_f32, long long M, int cols, cudaStream_t st) {
+  if (M <= 0) return 0;
+  l2norm_rows_kernel<<<static_cast<unsigned>((M + 3) / 4), 128, 0, st>>>(
+      in, ldi, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, out_f32, M, cols);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("l2norm launch failed");
+}
+
+int launch_colsum(const float* in, long long ldi, float* out, int rows, int cols, cudaStream_t st) {
+  if (cols <= 0) return 0;
+  colsum_kernel<<<(cols + 255) / 256, 256, 0, st>>>(in, ldi, out, rows, cols);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("colsum launch failed");
+}
+
+int launch_center_ema(float* center, const float* batch_sum, float denom, float momentum, int cols, cudaStream_t st) {
+  if (cols <= 0) return 0;
+  center_ema_kernel<<<(cols + 255) / 256, 256, 0, st>>>(center, batch_sum, 1.0f / denom, momentum, cols);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("center_ema launch failed");
+}
 
 int launch_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
                         long long ldo, int out_kind, long long lo_off, long long M, float eps, cudaStream_t st,
@@ -211,14 +301,14 @@ int launch_layernorm768(const float* x, long long ldx, const float* gamma, const
 }
 
 int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,
-                    cudaStream_t st) {
+                    const int* starts, cudaStream_t st) {
   if (H % 16 || W % 16) return set_error("im2col: H, W must be multiples of 16 (got %d x %d)", H, W);
   if (W % 4) return set_error("im2col: W must be a multiple of 4");
   const int gh = H / 16, gw = W / 16;
   const long long total = static_cast<long long>(B) * gh * gw * T * 96;
   if (total == 0) return 0;
   im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, H, W, gh, gw);
+      x, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, H, W, gh, gw, starts);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("im2col launch failed");
 }
@@ -253,9 +343,10 @@ int launch_cls_mean(const float* in, void* out, long long ldo, int split, long l
 }
 
 int launch_pair_loss(const float* s, long long lds, const float* t, long long ldt, const float* center, float tt,
-                     float ts, int dim, int pairs, float* loss, cudaStream_t st) {
+                     float ts, int dim, int pairs, float* loss, const int* s_idx, const int* t_idx, cudaStream_t st) {
   if (pairs <= 0) return 0;
-  pair_loss_kernel<<<(pairs + 3) / 4, 128, 0, st>>>(s, lds, t, ldt, center, 1.0f / tt, 1.0f / ts, dim, pairs, loss);
+  pair_loss_kernel<<<(pairs + 3) / 4, 128, 0, st>>>(s, lds, t, ldt, center, 1.0f / tt, 1.0f / ts, dim, pairs, loss,
+                                                    s_idx, t_idx);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("pair_loss launch failed");
 }

@@ -159,8 +159,23 @@ long long dvst_workspace_bytes(const dvst_model* h, int B, int T, int H, int W) 
   return static_cast<long long>(carve(*m, nullptr, B, T, H / 16, W / 16).total);
 }
 
+static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
+                        int get_all, void* workspace, long long workspace_bytes, void* stream);
+
 int dvst_forward_features(dvst_model* h, const float* x_in, int B, int T, int H, int W, float* out, int get_all,
                           void* workspace, long long workspace_bytes, void* stream) {
+  return forward_impl(h, x_in, nullptr, B, T, H, W, out, get_all, workspace, workspace_bytes, stream);
+}
+
+int dvst_forward_windows(dvst_model* h, const float* frames, int F, const int* starts, int n_clips, int T, int H,
+                         int W, float* out, void* workspace, long long workspace_bytes, void* stream) {
+  if (starts == nullptr) return set_error("dvst_forward_windows: null starts");
+  if (F < T) return set_error("dvst_forward_windows: video has %d frames, window needs %d", F, T);
+  return forward_impl(h, frames, starts, n_clips, T, H, W, out, 0, workspace, workspace_bytes, stream);
+}
+
+static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
+                        int get_all, void* workspace, long long workspace_bytes, void* stream) {
   if (h == nullptr) return set_error("dvst_forward_features: null handle");
   Model* m = reinterpret_cast<Model*>(h);
   if (!m->finalized) return set_error("dvst_forward_features: weights not finalized");
@@ -205,7 +220,7 @@ int dvst_forward_features(dvst_model* h, const float* x_in, int B, int T, int H,
 
   // ---- patch embedding + positional / temporal embedding (timesformer.py:203-209,287-323) ----
   DVST_TRY(launch_embed_table(m->pos, m->cfg.pos_grid, m->time_embed, m->cfg.num_frames, w.emb, gh, gw, T, st));
-  DVST_TRY(launch_im2col16(x_in, w.a, lda, split, D, B, T, H, W, st));
+  DVST_TRY(launch_im2col16(x_in, w.a, lda, split, D, B, T, H, W, starts, st));
   DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.emb, N * T, w.x, D, 1, 0));
   DVST_TRY(launch_broadcast_row768(m->cls_pos0, w.x + Mt * D, D, static_cast<int>(n_cls), st));
 

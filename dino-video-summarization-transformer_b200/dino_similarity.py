@@ -1,0 +1,240 @@
+"""Drop-in for the reference's dino_similarity.py: per-frame DINO-loss scoring of a video for adaptive frame selection.
+
+  * `DINOLoss`        - dino_similarity.py:120-135 (same constructor / forward / `center` buffer).
+  * `export_loss`     - dino_similarity.py:97-117 (same JSON read-modify-write format).
+  * `score_video`     - dino_similarity.py:66-93 for ONE video, restructured for the GPU: frames are uploaded once
+                        ([F,3,224,224], not the reference's [2F,3,G,224,224] padded views), windows are built on the
+                        device by index (dvst_forward_windows), identical windows are scored once (only F-2 student and
+                        max(F-G+1,1) teacher windows are distinct) and all F losses come back in a single D2H copy
+                        instead of one `.item()` sync per frame.  Results are unchanged: every frame's loss is the loss
+                        of exactly the (local, global) window pair the reference builds for it.
+  * `dino_similarity` - the driver loop over a dataset of videos.
+
+Mode R (reference-exact): loss over the 768-d backbone features, tau_t = 0.02, tau_s = 0.3, zero center.
+Mode H (north star): `head=DINOHead(768, 65536)`; features -> bottleneck -> fused last-layer GEMM + softmax + CE.
+"""
+import json
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class DINOLoss(nn.Module):
+    """calculates the DINO loss for two output tensors and returns a single value (dino_similarity.py:120-135)."""
+
+    def __init__(self, out_dim, teacher_temp, student_temp=0.1):
+        super().__init__()
+        self.student_temp = student_temp
+        self.register_buffer("center", torch.zeros(1, out_dim))
+        self.teacher_temp = teacher_temp
+
+    def pair_losses(self, student_output, teacher_output, s_idx=None, t_idx=None):
+        """Per-pair losses [P] for rows of student_output / teacher_output ([P, out_dim] fp32 CUDA tensors); optional
+        int32 row-gather indices pair student row s_idx[p] with teacher row t_idx[p]."""
+        if not student_output.is_cuda:
+            raise _lib.DvstError("dvst_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
+        s = student_output.detach().to(torch.float32)
+        t = teacher_output.detach().to(torch.float32)
+        s = s.reshape(-1, s.shape[-1]).contiguous()
+        t = t.reshape(-1, t.shape[-1]).contiguous()
+        dim = s.shape[-1]
+        if t.shape[-1] != dim or self.center.shape[-1] != dim:
+            raise ValueError("student / teacher / center dims differ")
+        P = s.shape[0] if s_idx is None else s_idx.numel()
+        if s_idx is None and t.shape[0] != P:
+            raise ValueError("student and teacher must hold the same number of rows")
+        out = torch.empty(P, dtype=torch.float32, device=s.device)
+        center = self.center.to(device=s.device, dtype=torch.float32).contiguous()
+        L = _lib.lib()
+        with torch.cuda.device(s.device):
+            if s_idx is None:
+                _lib.check(L.dvst_pair_loss(_lib.ptr(s), s.stride(0), _lib.ptr(t), t.stride(0), _lib.ptr(center),
+                                            float(self.teacher_temp), float(self.student_temp), dim, P, _lib.ptr(out),
+                                            _lib.cur_stream()))
+            else:
+                _lib.check(L.dvst_pair_loss_indexed(_lib.ptr(s), s.stride(0), _lib.ptr(s_idx), _lib.ptr(t),
+                                                    t.stride(0), _lib.ptr(t_idx), _lib.ptr(center),
+                                                    float(self.teacher_temp), float(self.student_temp), dim, P,
+                                                    _lib.ptr(out), _lib.cur_stream()))
+        return out
+
+    def forward(self, student_output, teacher_output):
+        # cross-entropy between softmax outputs for the teacher and student; `.mean()` over pairs like the reference
+        return self.pair_losses(student_output, teacher_output).mean()
+
+
+def export_loss(loss_list, video_path, file_path):
+    """exporting the loss values as a JSON file - same format and merge semantics as dino_similarity.py:97-117."""
+    video_name = os.path.basename(video_path)
+    video_name_without_extension, _ = os.path.splitext(video_name)
+    video_dict = {video_name_without_extension: loss_list}
+    if os.path.exists(file_path):
+        with open(file_path, 'r') as file:
+            data = json.load(file)
+        merged_dict = data.copy()
+        merged_dict.update(video_dict)
+        with open(file_path, 'w') as file:
+            json.dump(merged_dict, file)
+    else:
+        with open(file_path, 'w') as file:
+            json.dump(video_dict, file)
+
+
+def preprocess_frames(video_uint8, sampling_rate=4, mean=(0.45, 0.45, 0.45), std=(0.225, 0.225, 0.225), crop_size=224):
+    """Loader front half (datasets_custom/dino_loss_loader.py:80-92): raw decoded video uint8 [n,H,W,3] -> every
+    `sampling_rate`-th frame, /255, mean/std normalised (data_utils.py:308-325), T H W C -> T C H W, centre crop
+    (transform.py:206-249, spatial_idx=1).  Runs on whatever device the video tensor lives on (upload uint8, not fp32)."""
+    frames = video_uint8[::sampling_rate].to(torch.float32) / 255.0
+    frames = frames - torch.tensor(mean, dtype=torch.float32, device=frames.device)
+    frames = frames / torch.tensor(std, dtype=torch.float32, device=frames.device)
+    frames = frames.permute(0, 3, 1, 2)
+    h, w = frames.shape[2], frames.shape[3]
+    y0, x0 = int(math.ceil((h - crop_size) / 2)), int(math.ceil((w - crop_size) / 2))
+    return frames[:, :, y0:y0 + crop_size, x0:x0 + crop_size].contiguous()
+
+
+def window_starts(F, local_clip_size=3, global_clip_size=30):
+    """Window rule of get_views_of_video_same_size (datasets_custom/dino_loss_loader.py:126-171) as index arithmetic:
+    returns (G, local_starts[F], global_starts[F]); frame i is scored on frames [j, j+local) vs [l, l+G)."""
+    loc, glob = int(local_clip_size / 2), int(global_clip_size / 2)
+    G = min(global_clip_size, F)
+    ls, gs = [], []
+    for i in range(F):
+        j, k, l, m = i - loc, i + loc + 1, i - glob, i + glob
+        if j < 0:
+            j, k = 0, local_clip_size
+        if k >= F:
+            k, j = F, F - local_clip_size
+        if l < 0:
+            l, m = 0, G
+        if m >= F:
+            m, l = F, F - G
+        ls.append(j)
+        gs.append(l)
+    return G, ls, gs
+
+
+class HeadScorer:
+    """Mode-H loss: DINOHead bottleneck + fused last layer / softmax / cross-entropy (never materialises logits)."""
+
+    def __init__(self, head, teacher_temp=0.04, student_temp=0.1, center=None):
+        self.head, self.teacher_temp, self.student_temp, self.center = head, teacher_temp, student_temp, center
+
+    def pair_losses(self, feat_s, feat_t, s_idx, t_idx):
+        L = _lib.lib()
+        zs, _ = self.head.bottleneck(feat_s)
+        zt, _ = self.head.bottleneck(feat_t)
+        # gather rows per frame (tiny: [F, 256] bf16)
+        zs = zs[:, :256].index_select(0, s_idx.long()).contiguous()
+        zt = zt[:, :256].index_select(0, t_idx.long()).contiguous()
+        P = zs.shape[0]
+        w = self.head._packed["last_bf16"]
+        loss = torch.empty(P, dtype=torch.float32, device=zs.device)
+        nb = L.dvst_head_loss_scratch_bytes(P)
+        scratch = torch.empty(nb, dtype=torch.uint8, device=zs.device)
+        c = None if self.center is None else self.center.to(device=zs.device, dtype=torch.float32).reshape(-1).contiguous()
+        _lib.check(L.dvst_head_loss(_lib.ptr(zs), _lib.ptr(zt), zs.stride(0), _lib.ptr(w), _lib.ptr(c),
+                                    float(self.teacher_temp), float(self.student_temp), P, self.head.out_dim,
+                                    _lib.ptr(loss), _lib.ptr(scratch), nb, _lib.cur_stream()))
+        return loss
+
+
+def _forward_windows(model, frames, starts, T, max_clips):
+    """Features [len(starts), 768] of the T-frame windows of `frames` [F,3,H,W] starting at `starts` (python ints)."""
+    L = _lib.lib()
+    dev = frames.device
+    model._ensure_packed(dev)
+    F, _, H, W = frames.shape
+    n = len(starts)
+    out = torch.empty(n, model.embed_dim, dtype=torch.float32, device=dev)
+    starts_t = torch.tensor(starts, dtype=torch.int32, device=dev)
+    for c0 in range(0, n, max_clips):
+        nb = min(max_clips, n - c0)
+        need = L.dvst_workspace_bytes(model._handle, nb, T, H, W)
+        if model._workspace is None or model._workspace.numel() < need or model._workspace.device != dev:
+            model._workspace = None
+            model._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        _lib.check(L.dvst_forward_windows(model._handle, _lib.ptr(frames), F, _lib.ptr(starts_t[c0:]), nb, T, H, W,
+                                          _lib.ptr(out[c0:]), _lib.ptr(model._workspace), model._workspace.numel(),
+                                          _lib.cur_stream()))
+    return out
+
+
+def score_video_device(model, frames, dino_loss, local_clip_size=3, global_clip_size=30, scorer=None,
+                       max_rows=1 << 19):
+    """Scores one video on the GPU; returns the per-frame losses as a CUDA tensor [F] (no host sync).
+
+    model: dvst_b200 VisionTransformer; frames: fp32 [F,3,H,W] CUDA (normalised, cropped - what the reference's loader
+    produces before view construction, dino_loss_loader.py:80-92); dino_loss: DINOLoss (mode R) - ignored when a
+    HeadScorer is given (mode H)."""
+    if not frames.is_cuda:
+        raise _lib.DvstError("dvst_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
+    frames = frames.detach().to(torch.float32).contiguous()
+    F, _, H, W = frames.shape
+    dev = frames.device
+    with torch.cuda.device(dev):
+        if F < local_clip_size or H != 224 or W != 224:
+            # malformed video -> the reference's dummy views: `global_clip_size` identical losses of the all-zero
+            # (T=local, T=60) pair (dino_loss_loader.py:36-38,103-107; dino_similarity.py:78)
+            zs = torch.zeros(local_clip_size, 3, 224, 224, device=dev)
+            zt = torch.zeros(60, 3, 224, 224, device=dev)
+            fs = _forward_windows(model, zs, [0], local_clip_size, 1)
+            ft = _forward_windows(model, zt, [0], 60, 1)
+            idx = torch.zeros(global_clip_size, dtype=torch.int32, device=dev)
+            if scorer is not None:
+                return scorer.pair_losses(fs, ft, idx, idx)
+            return dino_loss.pair_losses(fs, ft, idx, idx)
+        G, ls, gs = window_starts(F, local_clip_size, global_clip_size)
+        s_starts = sorted(set(ls))
+        t_starts = sorted(set(gs))
+        N = (H // 16) * (W // 16)
+        fs = _forward_windows(model, frames, s_starts, local_clip_size, max(1, max_rows // (N * local_clip_size)))
+        ft = _forward_windows(model, frames, t_starts, G, max(1, max_rows // (N * G)))
+        s_pos = {v: i for i, v in enumerate(s_starts)}
+        t_pos = {v: i for i, v in enumerate(t_starts)}
+        s_idx = torch.tensor([s_pos[j] for j in ls], dtype=torch.int32, device=dev)
+        t_idx = torch.tensor([t_pos[l] for l in gs], dtype=torch.int32, device=dev)
+        if scorer is not None:
+            return scorer.pair_losses(fs, ft, s_idx, t_idx)
+        return dino_loss.pair_losses(fs, ft, s_idx, t_idx)
+
+
+def score_video(model, frames, dino_loss=None, local_clip_size=3, global_clip_size=30, scorer=None, **kw):
+    """Python list of per-frame losses (what the reference appends via `.item()`, dino_similarity.py:87-88)."""
+    if dino_loss is None and scorer is None:
+        dino_loss = DINOLoss(out_dim=768, teacher_temp=0.02, student_temp=0.3).to(frames.device)
+    return score_video_device(model, frames, dino_loss, local_clip_size, global_clip_size, scorer, **kw).tolist()
+
+
+def dino_similarity(cfg, local_clip_size, global_clip_size, sampling_rate, file_path, dataset=None, model=None,
+                    scorer=None):
+    """Driver with the reference's signature (dino_similarity.py:16-93).
+
+    Video decoding is outside the accelerated path: `dataset` is any iterable of
+    (frames [F,3,224,224] fp32 already sub-sampled by `sampling_rate`, normalised and centre-cropped, file_name).  When
+    `model` is None it is built exactly like the reference does (get_vit_base_patch16_224 + "backbone."-stripped
+    checkpoint from cfg.pretrained_weights)."""
+    from .models import get_vit_base_patch16_224
+    if dataset is None:
+        raise ValueError("pass `dataset`: an iterable of (frames, file_name); video decoding is not part of this path")
+    if model is None:
+        model = get_vit_base_patch16_224(cfg=cfg, no_head=False)
+        if getattr(cfg, "pretrained_weights", None):
+            ckpt = torch.load(cfg.pretrained_weights, map_location="cpu")
+            renamed = {x[len("backbone."):]: y for x, y in ckpt.items() if x.startswith("backbone.")}
+            model.load_state_dict(renamed, strict=False)
+        model = model.eval().cuda()
+    dev = next(model.parameters()).device
+    dino_loss = DINOLoss(out_dim=768, teacher_temp=0.02, student_temp=0.3).to(dev)
+    results = {}
+    for i, (frames, file_name) in enumerate(dataset):
+        with torch.no_grad():
+            loss = score_video(model, frames.to(dev, non_blocking=True), dino_loss, local_clip_size, global_clip_size,
+                               scorer=scorer)
+        export_loss(loss, file_name, file_path)
+        results[os.path.splitext(os.path.basename(file_name))[0]] = loss
+    return results

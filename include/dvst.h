@@ -66,11 +66,47 @@ long long dvst_workspace_bytes(const dvst_model* m, int B, int T, int H, int W);
 int dvst_forward_features(dvst_model* m, const float* x, int B, int T, int H, int W, float* out, int get_all,
                           void* workspace, long long workspace_bytes, void* stream);
 
+/* Device-side view construction + forward: `frames` is a frame-major video fp32 [F,3,H,W]; clip b is the window of T
+ * consecutive frames starting at starts[b] (int32 device array, n_clips entries).  Replaces the materialised
+ * [2F,3,G,224,224] view tensor of get_views_of_video_same_size (datasets_custom/dino_loss_loader.py:126-171) followed by
+ * model(views) (dino_similarity.py:78-84).  out fp32 [n_clips,768].  Workspace as for B = n_clips. */
+int dvst_forward_windows(dvst_model* m, const float* frames, int F, const int* starts, int n_clips, int T, int H,
+                         int W, float* out, void* workspace, long long workspace_bytes, void* stream);
+
 /* Scoring DINOLoss.forward for `pairs` rows at once - dino_similarity.py:129-135:
  *   loss[p] = sum_j -softmax((t[p]-center)/teacher_temp)_j * log_softmax(s[p]/student_temp)_j
  * student / teacher fp32 [pairs, dim] (row strides lds / ldt), center fp32 [dim] or NULL (zeros), loss fp32 [pairs]. */
 int dvst_pair_loss(const float* student, long long lds, const float* teacher, long long ldt, const float* center,
                    float teacher_temp, float student_temp, int dim, int pairs, float* loss, void* stream);
+
+/* "Mode H": DINOHead last layer (weight-normalised 256 -> out_dim, vision_transformer.py:266-282) fused with the
+ * centred / sharpened softmax cross-entropy above; the out_dim-wide logits are never written to memory.
+ *   zs, zt : bf16 [pairs, ldz] L2-normalised bottleneck vectors (256 wide) of the student / teacher views
+ *   w      : bf16 [out_dim, 256] = weight_g * weight_v / ||weight_v||_row     (out_dim multiple of 64)
+ *   center : fp32 [out_dim] or NULL;  loss fp32 [pairs];  scratch >= dvst_head_loss_scratch_bytes(pairs) bytes. */
+long long dvst_head_loss_scratch_bytes(int pairs);
+int dvst_head_loss(const void* zs, const void* zt, long long ldz, const void* w, const float* center,
+                   float teacher_temp, float student_temp, int pairs, int out_dim, float* loss, void* scratch,
+                   long long scratch_bytes, void* stream);
+
+/* Same with row gathers: pair p uses student row s_idx[p] and teacher row t_idx[p] (int32 device arrays or NULL).
+ * Covers the per-frame pairing of dino_similarity.py:87-88 over de-duplicated window features and the (iq, v != iq)
+ * terms of the training DINOLoss (train_ssl.py:660-667). */
+int dvst_pair_loss_indexed(const float* student, long long lds, const int* s_idx, const float* teacher, long long ldt,
+                           const int* t_idx, const float* center, float teacher_temp, float student_temp, int dim,
+                           int pairs, float* loss, void* stream);
+
+/* DINOLoss.update_center pieces (train_ssl.py:686-691): out[c] = sum_r in[r,c];  center = center*momentum +
+ * (batch_sum/denom)*(1-momentum).  The all_reduce between them stays in torch.distributed (NCCL). */
+int dvst_colsum(const float* in, long long ldi, float* out, int rows, int cols, void* stream);
+int dvst_center_ema(float* center, const float* batch_sum, float denom, float momentum, int cols, void* stream);
+
+/* fp32 [M,cols] -> bf16 GEMM operand (split: also the rounding residual at column + lo_off). */
+int dvst_cast_bf16(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off, long long M,
+                   int cols, void* stream);
+/* F.normalize(x, dim=-1, p=2) (vision_transformer.py:280): bf16 (+lo) rows for the last-layer GEMM, optional fp32 copy. */
+int dvst_l2norm_rows(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off,
+                     float* out_f32, long long M, int cols, void* stream);
 
 /* ---- building blocks (exported for unit tests and the DINO head) -------------------------------------------------- */
 /* out[M,N] = epilogue(A[M,K] x W[N,K]^T).  bf16 operands, fp32 accumulate (tcgen05 / TMEM).
