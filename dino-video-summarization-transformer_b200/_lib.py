@@ -27,6 +27,8 @@ SIGNATURES = {
     "dvst_abi_version": (c_int, []),
     "dvst_gemm_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
                                c_void_p, c_ll, c_int, c_ll, c_int, c_void_p]),
+    "dvst_profile_enable": (None, [c_int]),
+    "dvst_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "dvst_create": (c_int, [c_void_p, c_void_p]),
     "dvst_destroy": (None, [c_void_p]),
     "dvst_set_weight": (c_int, [c_void_p, ctypes.c_char_p, c_void_p]),
@@ -76,6 +78,21 @@ def check(rc):
 
 def launch_count():
     return int(lib().dvst_launch_count())
+
+
+PROF_KINDS = ("gemm", "attention", "layernorm", "elementwise", "head_loss")
+
+
+def profile_enable(on):
+    lib().dvst_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{kind: (ms, work, launches)} since the last collect (waits for the recorded events)."""
+    n = len(PROF_KINDS)
+    ms, work, cnt = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_longlong * n)()
+    check(lib().dvst_profile_collect(ms, work, cnt, n))
+    return {k: (ms[i], work[i], int(cnt[i])) for i, k in enumerate(PROF_KINDS)}
 
 
 def ptr(t):

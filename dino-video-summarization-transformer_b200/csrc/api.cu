@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "../../include/dvst.h"
 #include "dvst_internal.h"
@@ -21,6 +23,32 @@ int set_error(const char* fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+struct ProfRec { int kind; double work; cudaEvent_t e0, e1; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_prof_mu;
+
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+ProfScope::ProfScope(int kind, double work, cudaStream_t stream) : idx(-1), st(stream) {
+  if (!g_prof) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{kind, work, get_event(), get_event()};
+  cudaEventRecord(r.e0, st);
+  g_recs.push_back(r);
+  idx = static_cast<int>(g_recs.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_recs[idx].e1, st);
+}
+
 }  // namespace dvst
 
 using namespace dvst;
@@ -30,6 +58,26 @@ extern "C" {
 const char* dvst_last_error(void) { return g_err; }
 long long dvst_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int dvst_abi_version(void) { return DVST_ABI_VERSION; }
+
+void dvst_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof = on != 0;
+}
+
+int dvst_profile_collect(double* ms, double* work, long long* count, int nkinds) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int k = 0; k < nkinds; ++k) { ms[k] = 0; work[k] = 0; count[k] = 0; }
+  for (auto& r : g_recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess)
+      return set_error("dvst_profile_collect: event query failed");
+    if (r.kind < nkinds) { ms[r.kind] += t; work[r.kind] += r.work; count[r.kind] += 1; }
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_recs.clear();
+  return 0;
+}
 
 int dvst_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
                    int split, const float* residual, long long ldr, void* out, long long ldo, int out_kind,

@@ -265,6 +265,7 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
   const int S_pad = (p.S + 15) & ~15;
   const long long n_prob = static_cast<long long>(p.n_seq) * p.heads;
   cudaError_t e;
+  ProfScope prof(PROF_ATTENTION, 4.0 * p.n_seq * p.heads * static_cast<double>(p.S) * p.S * HD, st);
   if (mode == 0) {
     const size_t smem = static_cast<size_t>(4) * 2 * S_pad * 128;
     if (smem > 200 * 1024) return set_error("temporal attention: T=%d too long for the per-warp K/V staging", T);

@@ -13,6 +13,16 @@ int set_error(const char* fmt, ...);
 void count_launch();
 int num_sms();
 
+// Optional live per-kernel timing (CUDA events on the launching stream), used by bench.py for the roofline figures.
+enum ProfKind { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ELEMENTWISE = 3, PROF_HEAD_LOSS = 4,
+                PROF_NKINDS = 5 };
+struct ProfScope {
+  int idx;
+  cudaStream_t st;
+  ProfScope(int kind, double work, cudaStream_t stream);  // work: FLOPs (GEMM / attention) or bytes (others)
+  ~ProfScope();
+};
+
 struct GemmArgs {
   const void* A = nullptr;  // bf16 [M, lda]  (split: [hi | lo], lo at column K)
   long long lda = 0;

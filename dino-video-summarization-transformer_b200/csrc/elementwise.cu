@@ -294,6 +294,7 @@ int launch_layernorm768(const float* x, long long ldx, const float* gamma, const
                         long long rm_group, long long rm_stride, long long rm_offset) {
   if (M <= 0) return 0;
   const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+  ProfScope prof(PROF_LAYERNORM, static_cast<double>(M) * D * (4.0 + (out_kind == 1 ? 4.0 : out_kind == 2 ? 4.0 : 2.0)), st);
   layernorm768_kernel<<<grid, 256, 0, st>>>(x, ldx, gamma, beta, out, ldo, out_kind, lo_off, M, eps, rm_group,
                                             rm_stride, rm_offset);
   count_launch();
@@ -307,6 +308,7 @@ int launch_im2col16(const float* x, void* out, long long ldo, int split, long lo
   const int gh = H / 16, gw = W / 16;
   const long long total = static_cast<long long>(B) * gh * gw * T * 96;
   if (total == 0) return 0;
+  ProfScope prof(PROF_ELEMENTWISE, static_cast<double>(total) * 8 * (4.0 + (split ? 4.0 : 2.0)), st);
   im2col16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
       x, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, H, W, gh, gw, starts);
   count_launch();

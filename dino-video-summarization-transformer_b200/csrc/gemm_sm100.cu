@@ -325,6 +325,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   p.num_n_blocks = g.N / BN;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  ProfScope prof(PROF_GEMM, 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
   gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));

@@ -236,6 +236,7 @@ int launch_head_loss(const void* zs, const void* zt, long long ldz, const void* 
   if (gx < 1) gx = 1;
   if (gx > p.n_tiles) gx = p.n_tiles;
   dim3 grid(gx, m_tiles);
+  ProfScope prof(PROF_HEAD_LOSS, static_cast<double>(out_dim) * HK * 2.0 * m_tiles + 2.0 * P * HK * 2.0, st);
   head_loss_kernel<<<grid, H_THREADS, H_SMEM, st>>>(tmS, tmT, tmW, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("head_loss launch: %s", cudaGetErrorString(e));

@@ -42,6 +42,12 @@ const char* dvst_last_error(void);
 long long dvst_launch_count(void);
 int dvst_abi_version(void);
 
+/* Live per-kernel timing for bench.py's roofline: while enabled, every launch is bracketed by CUDA events on its own
+ * stream.  dvst_profile_collect waits for the recorded events, sums elapsed ms / work (FLOPs for kind 0 GEMM and
+ * 1 attention, bytes for 2 layernorm, 3 elementwise, 4 head-loss) / launch counts per kind, and clears the log. */
+void dvst_profile_enable(int on);
+int dvst_profile_collect(double* ms, double* work, long long* count, int nkinds);
+
 /* ---- model handle: replaces VisionTransformer.__init__/load_state_dict (models/timesformer.py:212-263) ----------- */
 int dvst_create(const dvst_config* cfg, dvst_model** out);
 void dvst_destroy(dvst_model* m);

@@ -1,0 +1,188 @@
+"""Kernel-level parity through the C ABI on a B200 (each kernel vs a plain fp32 torch statement of the same op)."""
+import pytest
+import torch
+
+import dvst_b200  # noqa: F401
+from dvst_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _gemm(A, W, bias=None, residual=None, out_kind=0, act=0, split=0, K=None):
+    L = _lib.lib()
+    M, N = A.shape[0], W.shape[0]
+    K = K or A.shape[1]
+    shape = (M, 2 * N) if out_kind == 2 else (M, N)
+    out = torch.empty(shape, device=A.device, dtype=torch.float32 if out_kind == 1 else torch.bfloat16)
+    _lib.check(L.dvst_gemm_bf16(_lib.ptr(A), A.stride(0), _lib.ptr(W), W.stride(0), _lib.ptr(bias), M, N, K, split,
+                                _lib.ptr(residual), residual.stride(0) if residual is not None else 0,
+                                _lib.ptr(out), shape[1], out_kind, N, act, _lib.cur_stream()))
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 256, 64), (127, 256, 128), (128, 768, 768), (333, 2304, 768), (4099, 3072, 768),
+                                   (2051, 768, 3072), (64, 65536, 256)])
+def test_gemm_epilogues(dev, M, N, K):
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    ref = A.float() @ W.float().t() + bias
+    assert _rel(_gemm(A, W, bias, out_kind=1), ref) < 1e-5          # fp32 out: only summation order differs
+    assert _rel(_gemm(A, W, bias, out_kind=0).float(), ref) < 4e-3  # bf16 rounding of the output
+    assert _rel(_gemm(A, W, bias, out_kind=0, act=1).float(), torch.nn.functional.gelu(ref)) < 4e-3
+    res = torch.randn(M, N, device=dev)
+    x = res.clone()
+    L = _lib.lib()
+    _lib.check(L.dvst_gemm_bf16(_lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(bias), M, N, K, 0, _lib.ptr(x), N,
+                                _lib.ptr(x), N, 1, 0, 0, _lib.cur_stream()))
+    assert _rel(x, ref + res) < 1e-5                                 # in-place residual
+
+
+def test_gemm_split_precision(dev):
+    torch.manual_seed(1)
+    M, N, K = 777, 768, 768
+    Af, Wf = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev) * 0.05
+
+    def hilo(t):
+        hi = t.bfloat16()
+        return torch.cat([hi, (t - hi.float()).bfloat16()], 1).contiguous()
+    ref = Af.double() @ Wf.double().t()
+    out = _gemm(hilo(Af), hilo(Wf), out_kind=1, split=1, K=K)
+    assert _rel(out, ref) < 2e-5
+    pair = _gemm(hilo(Af), hilo(Wf), out_kind=2, split=1, K=K)
+    assert _rel(pair[:, :N].float() + pair[:, N:].float(), ref) < 2e-5
+    assert _rel(_gemm(Af.bfloat16(), Wf.bfloat16(), out_kind=1), ref) > 5e-4  # plain bf16 operands are ~100x worse
+
+
+def test_gemm_rejects_bad_shapes(dev):
+    A = torch.zeros(8, 64, device=dev, dtype=torch.bfloat16)
+    W = torch.zeros(100, 64, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(_lib.DvstError, match="multiple of 256"):
+        _gemm(A, W)
+
+
+def test_layernorm(dev):
+    torch.manual_seed(0)
+    L = _lib.lib()
+    for M in (1, 7, 1000):
+        x = torch.randn(M, 768, device=dev) * 3 + 0.5
+        g, b = torch.randn(768, device=dev), torch.randn(768, device=dev)
+        ref = torch.nn.functional.layer_norm(x, (768,), g, b, 1e-6)
+        o32 = torch.empty(M, 768, device=dev)
+        _lib.check(L.dvst_layernorm768(_lib.ptr(x), 768, _lib.ptr(g), _lib.ptr(b), _lib.ptr(o32), 768, 1, 0, M, 1e-6,
+                                       _lib.cur_stream()))
+        assert (o32 - ref).abs().max().item() < 2e-5
+        o = torch.empty(M, 1536, device=dev, dtype=torch.bfloat16)
+        _lib.check(L.dvst_layernorm768(_lib.ptr(x), 768, _lib.ptr(g), _lib.ptr(b), _lib.ptr(o), 1536, 2, 768, M, 1e-6,
+                                       _lib.cur_stream()))
+        assert (o[:, :768].float() + o[:, 768:].float() - ref).abs().max().item() < 1e-4
+
+
+def _attn_ref(q, k, v):
+    S = q.shape[0]
+    qh, kh, vh = (t.reshape(t.shape[0], 12, 64).transpose(0, 1).float() for t in (q, k, v))
+    p = torch.softmax(qh @ kh.transpose(1, 2) * 0.125, dim=-1)
+    return (p @ vh).transpose(0, 1).reshape(S, 768)
+
+
+@pytest.mark.parametrize("mode,B,T,N", [(0, 2, 16, 9), (0, 1, 3, 5), (0, 1, 30, 4), (0, 1, 60, 2), (0, 1, 1, 3),
+                                        (1, 2, 3, 196), (1, 1, 2, 36), (2, 2, 2, 196), (3, 2, 2, 196)])
+def test_attention_modes(dev, mode, B, T, N):
+    torch.manual_seed(mode * 100 + T)
+    L = _lib.lib()
+    Mt = B * N * T
+    ncls = B * T if mode == 3 else B
+    qkv = (torch.randn(Mt + ncls, 2304, device=dev) * 1.5).bfloat16()
+    out = torch.zeros(Mt + ncls, 768, device=dev, dtype=torch.bfloat16)
+    cls_out = torch.zeros(B, T, 768, device=dev)
+    _lib.check(L.dvst_attention(_lib.ptr(qkv), 2304, _lib.ptr(out), 768, _lib.ptr(cls_out), mode, B, T, N, Mt,
+                                _lib.cur_stream()))
+    q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
+    refo = torch.zeros(Mt + ncls, 768, device=dev)
+    refc = torch.zeros(B, T, 768, device=dev)
+    rows = torch.arange(Mt, device=dev).reshape(B, N, T)
+    for bb in range(B):
+        if mode == 0:
+            for n in range(N):
+                r = rows[bb, n]
+                refo[r] = _attn_ref(q[r], k[r], v[r])
+        elif mode in (1, 3):
+            for t in range(T):
+                c = Mt + (bb * T + t if mode == 3 else bb)
+                r = torch.cat([torch.tensor([c], device=dev), rows[bb, :, t]])
+                o = _attn_ref(q[r], k[r], v[r])
+                refo[r[1:]] = o[1:]
+                if mode == 1:
+                    refc[bb, t] = o[0]
+                else:
+                    refo[c] = o[0]
+        else:
+            r = torch.cat([torch.tensor([Mt + bb], device=dev), rows[bb].reshape(-1)])
+            refo[r] = _attn_ref(q[r], k[r], v[r])
+    if mode == 1:
+        assert _rel(cls_out, refc) < 5e-3
+        assert _rel(out[:Mt].float(), refo[:Mt]) < 5e-3
+        assert float(out[Mt:].float().abs().sum()) == 0  # shared CLS rows are not written by the spatial kernel
+    else:
+        assert _rel(out.float(), refo) < 5e-3
+
+
+def test_pair_loss_and_indexed(dev):
+    torch.manual_seed(3)
+    L = _lib.lib()
+    for dim in (768, 65536):
+        s, t = torch.randn(9, dim, device=dev), torch.randn(5, dim, device=dev)
+        c = torch.randn(dim, device=dev) * 0.1
+        si = torch.tensor([0, 1, 8, 3, 3, 2], dtype=torch.int32, device=dev)
+        ti = torch.tensor([4, 0, 0, 1, 2, 2], dtype=torch.int32, device=dev)
+        out = torch.empty(6, device=dev)
+        _lib.check(L.dvst_pair_loss_indexed(_lib.ptr(s), dim, _lib.ptr(si), _lib.ptr(t), dim, _lib.ptr(ti), _lib.ptr(c),
+                                            0.04, 0.1, dim, 6, _lib.ptr(out), _lib.cur_stream()))
+        ss, tt = s[si.long()].double(), t[ti.long()].double()
+        ref = -(torch.softmax((tt - c.double()) / 0.04, -1) * torch.log_softmax(ss / 0.1, -1)).sum(-1)
+        assert ((out.double() - ref).abs() / ref.abs()).max().item() < 1e-5
+
+
+@pytest.mark.parametrize("P,out_dim", [(1, 4096), (37, 65536), (128, 8192), (200, 4096)])
+def test_fused_head_loss(dev, P, out_dim):
+    """Fused last-layer GEMM + softmax + CE against the materialised fp64 statement on the same bf16 operands."""
+    torch.manual_seed(P)
+    L = _lib.lib()
+    zs = torch.nn.functional.normalize(torch.randn(P, 256, device=dev), dim=-1).bfloat16()
+    zt = torch.nn.functional.normalize(torch.randn(P, 256, device=dev), dim=-1).bfloat16()
+    w = torch.nn.functional.normalize(torch.randn(out_dim, 256, device=dev), dim=-1).bfloat16()
+    c = torch.randn(out_dim, device=dev) * 0.05
+    for (tt, ts, cc) in [(0.04, 0.1, c), (0.02, 0.3, None)]:
+        loss = torch.empty(P, device=dev)
+        nb = L.dvst_head_loss_scratch_bytes(P)
+        scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _lib.check(L.dvst_head_loss(_lib.ptr(zs), _lib.ptr(zt), 256, _lib.ptr(w), _lib.ptr(cc), tt, ts, P, out_dim,
+                                    _lib.ptr(loss), _lib.ptr(scratch), nb, _lib.cur_stream()))
+        ls, lt = zs.double() @ w.double().t(), zt.double() @ w.double().t()
+        cd = torch.zeros(out_dim, device=dev, dtype=torch.float64) if cc is None else cc.double()
+        ref = -(torch.softmax((lt - cd) / tt, -1) * torch.log_softmax(ls / ts, -1)).sum(-1)
+        assert ((loss.double() - ref).abs() / ref.abs()).max().item() < 2e-5
+
+
+def test_colsum_and_center_ema(dev):
+    torch.manual_seed(0)
+    L = _lib.lib()
+    t = torch.randn(6, 4096, device=dev)
+    bs = torch.empty(4096, device=dev)
+    _lib.check(L.dvst_colsum(_lib.ptr(t), 4096, _lib.ptr(bs), 6, 4096, _lib.cur_stream()))
+    assert torch.allclose(bs, t.sum(0), atol=1e-5)
+    center = torch.randn(4096, device=dev)
+    ref = center * 0.9 + bs / 12.0 * 0.1
+    _lib.check(L.dvst_center_ema(_lib.ptr(center), _lib.ptr(bs), 12.0, 0.9, 4096, _lib.cur_stream()))
+    assert torch.allclose(center, ref, atol=1e-6)

@@ -1,0 +1,130 @@
+"""Host-side mirror of the reference interfaces (no GPU): state_dict key parity, window / selection logic vs the
+reference goldens, JSON export format, sharding, and 'fails loudly on CPU'."""
+import json
+import os
+import types
+from functools import partial
+
+import pytest
+import torch
+
+import dvst_b200  # noqa: F401
+from dvst_b200 import _lib
+from dvst_b200.dino_similarity import DINOLoss, export_loss, preprocess_frames, window_starts
+from dvst_b200.frame_selection import select_frames_adaptive, select_frames_uniform
+from dvst_b200.models import TimeSformer, VisionTransformer, get_vit_base_patch16_224, vit_base_patch16_224
+from dvst_b200.parallel import shard_videos, video_cost
+from dvst_b200.testing import synth_backbone_state_dict, synth_head_state_dict
+from dvst_b200.utils import MultiCropWrapper
+from dvst_b200.vision_transformer import DINOHead
+
+
+def _cfg(att="divided_space_time"):
+    return types.SimpleNamespace(DATA=types.SimpleNamespace(TRAIN_CROP_SIZE=224, NUM_FRAMES=8),
+                                 MODEL=types.SimpleNamespace(NUM_CLASSES=400),
+                                 TIMESFORMER=types.SimpleNamespace(ATTENTION_TYPE=att, PRETRAINED_MODEL=""))
+
+
+def test_factory_matches_reference_interface():
+    m = get_vit_base_patch16_224(_cfg(), no_head=False)
+    assert sum(p.numel() for p in m.parameters()) == 121566352  # 121.57 M
+    assert m.embed_dim == m.num_features == 768 and m.num_patches == 196
+    assert m.attention_type == "divided_space_time" and len(m.blocks) == 12
+    # reference init quirk: temporal_fc of ALL blocks and time_embed are zero
+    assert all(float(b.temporal_fc.weight.detach().abs().sum()) == 0 for b in m.blocks)
+    assert float(m.time_embed.detach().abs().sum()) == 0
+    res = m.load_state_dict(synth_backbone_state_dict(0, num_classes=400), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert get_vit_base_patch16_224(_cfg(), no_head=True).head is None
+    # checkpoint loading path of the drivers: strict=False after the "backbone." strip
+    ck = {"backbone." + k: v for k, v in synth_backbone_state_dict(0).items()}
+    ren = {k[len("backbone."):]: v for k, v in ck.items() if k.startswith("backbone.")}
+    assert set(m.load_state_dict(ren, strict=False).missing_keys) == {"head.weight", "head.bias"}
+
+
+@pytest.mark.parametrize("att", ["joint_space_time", "space_only"])
+def test_other_attention_types_keys(att):
+    m = VisionTransformer(num_classes=0, depth=2, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                          attention_type=att)
+    m.load_state_dict(synth_backbone_state_dict(0, depth=2, attention_type=att), strict=True)
+
+
+def test_wrappers_and_unsupported_configs():
+    assert isinstance(TimeSformer(num_classes=0).model, VisionTransformer)
+    assert isinstance(vit_base_patch16_224(_cfg()).model, VisionTransformer)
+    with pytest.raises(ValueError):
+        VisionTransformer(embed_dim=384, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    with pytest.raises(ValueError):
+        VisionTransformer(qkv_bias=True)  # default LayerNorm eps 1e-5 is not what the reference builds
+
+
+def test_cpu_input_fails_loudly():
+    m = VisionTransformer(num_classes=0, depth=1, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    with pytest.raises(_lib.DvstError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 2, 224, 224))
+    with pytest.raises(_lib.DvstError, match="no CPU fallback"):
+        DINOLoss(768, 0.02, 0.3)(torch.zeros(768), torch.zeros(768))
+    with pytest.raises(_lib.DvstError, match="no CPU fallback"):
+        DINOHead(768, 1024)(torch.zeros(2, 768))
+
+
+def test_dino_head_keys_and_loss_buffer():
+    h = DINOHead(768, 65536)
+    assert sum(p.numel() for p in h.parameters()) == 23138560  # 23.14 M (incl. weight_g)
+    res = h.load_state_dict(synth_head_state_dict(2), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert float(h.last_layer.weight_g.min()) == 1.0 and not h.last_layer.weight_g.requires_grad
+    L = DINOLoss(out_dim=768, teacher_temp=0.02, student_temp=0.3)
+    assert tuple(L.center.shape) == (1, 768) and "center" in L.state_dict()
+
+
+def test_window_rule_and_selection_vs_reference_goldens(golden_dir):
+    W = json.load(open(os.path.join(golden_dir, "windows.json")))
+    for F, c in W.items():
+        G, ls, gs = window_starts(int(F))
+        assert G == c["G"] and [list(p) for p in zip(ls, gs)] == [list(p) for p in c["starts"]]
+        # only F-2 student and max(F-G+1, 1) teacher windows are distinct (SURVEY finding 5)
+        assert len(set(ls)) == int(F) - 2 and len(set(gs)) == max(int(F) - G + 1, 1)
+    S = json.load(open(os.path.join(golden_dir, "selection.json")))
+    for name, c in S.items():
+        for N in (8, 16):
+            assert select_frames_adaptive(c["loss"], c["n_unsampled"], 4, N) == c[f"idx{N}"], name
+    assert select_frames_uniform(75, 8) == [0, 9, 18, 27, 36, 45, 54, 63]
+
+
+def test_export_loss_format(tmp_path):
+    p = str(tmp_path / "loss.json")
+    export_loss([1.0, 2.5], "/data/vids/abc_1_2.avi", p)
+    export_loss([3.0], "/x/def.mp4", p)
+    export_loss([9.0], "abc_1_2.avi", p)  # read-modify-write: later result replaces the earlier one
+    assert open(p).read() == '{"abc_1_2": [9.0], "def": [3.0]}'
+
+
+def test_preprocess_frames():
+    raw = torch.randint(0, 256, (10, 240, 320, 3), dtype=torch.uint8)
+    f = preprocess_frames(raw, 4)
+    assert tuple(f.shape) == (3, 3, 224, 224)
+    ref = ((raw[4, 8 + 5, 48 + 7, 1].float() / 255.0) - 0.45) / 0.225
+    assert abs(float(f[1, 1, 5, 7]) - float(ref)) < 1e-6
+
+
+def test_sharding_is_balanced_and_complete():
+    lens = [30, 68, 75, 11, 450, 38, 38, 53, 2, 300, 120, 64]
+    for world in (1, 2, 4, 8):
+        parts = shard_videos(lens, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(lens)))
+        loads = [sum(video_cost(lens[i]) for i in p) for p in parts]
+        assert max(loads) <= sum(loads) / world + max(video_cost(f) for f in lens)
+
+
+def test_multicrop_wrapper_groups_by_resolution():
+    calls = []
+
+    class Fake(torch.nn.Module):
+        def forward(self, x):
+            calls.append(tuple(x.shape))
+            return x.flatten(1)[:, :4]
+    w = MultiCropWrapper(Fake(), torch.nn.Identity())
+    views = [torch.zeros(2, 3, 8, 224, 224)] * 2 + [torch.zeros(2, 3, 8, 96, 96)] * 3
+    out = w(views)
+    assert calls == [(4, 3, 8, 224, 224), (6, 3, 8, 96, 96)] and tuple(out.shape) == (10, 4)
