@@ -41,6 +41,7 @@ struct GemmArgs {
   int split = 0;
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+void set_gemm_cta_group(int cg);  // 1 or 2 (default 2); tuning / test hook
 
 int launch_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
                         long long ldo, int out_kind, long long lo_off, long long M, float eps, cudaStream_t st,

@@ -7,9 +7,10 @@
 // to tcgen05.mma without any transpose.  Accumulators live in TMEM (2 x 256 fp32 columns, double buffered so the
 // epilogue of tile i overlaps the MMAs of tile i+1).
 //
-// Warp roles (384 threads, 1 CTA / SM, grid = #SMs, static round-robin tile schedule):
-//   warp 0      : TMA producer (one lane)       - 4-stage ring of {A 128x64, W 256x64} bf16 tiles (48 KiB / stage)
-//   warp 1      : MMA issuer (one lane)         - 4 x tcgen05.mma 128x256x16 per stage, tcgen05.commit -> mbarriers
+// Two variants of one template: 1-CTA (128x256 tiles) and 2-CTA cta_group::2 pairs (256x256 tiles, W tile split
+// between the two CTAs' shared memories).  Warp roles (384 threads, 1 CTA / SM, grid = #SMs, static round-robin tiles):
+//   warp 0      : TMA producer (one lane)       - ring of {A 128x64, W 256x64 (or its 128-row half)} bf16 tiles
+//   warp 1      : MMA issuer (one lane, leader) - 4 x tcgen05.mma (128|256)x256x16 per stage, tcgen05.commit -> mbarriers
 //   warp 2      : TMEM allocator / deallocator
 //   warps 4..11 : epilogue                      - tcgen05.ld 32x32b.x32 -> bias / GELU -> per-warp smem transpose ->
 //                                                 coalesced residual read + store (fp32, bf16, or bf16 hi/lo pair)
@@ -24,21 +25,29 @@ namespace dvst {
 
 namespace {
 
-constexpr int BM = 128;
+constexpr int BM = 128;   // rows per CTA tile (a CTA pair covers 256 rows in 2-CTA mode)
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int EPI_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STG_STRIDE = 20;  // fp32 words per staged row (16 payload + 4 pad): conflict-free 128-bit STS/LDS
 constexpr int STG_BYTES = 32 * STG_STRIDE * 4;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256 /*barriers*/;
+
+// kCG = 1: one CTA per 128x256 tile, each CTA stages the whole 256-row W tile (48 KiB / stage, 4 stages).
+// kCG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256x256 tile; each CTA stages its 128 A rows and
+//          HALF of the W tile (32 KiB / stage, 6 stages) - the tensor core reads the other half from the peer's shared
+//          memory, which halves the L2->SM operand traffic per FLOP (the 1-CTA kernel saturates L2 bandwidth).
+template <int kCG> struct Cfg {
+  static constexpr int B_ROWS = BN / kCG;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = kCG == 1 ? 4 : 6;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256;
+};
 
 struct GemmParams {
   int M, N, K;
@@ -52,19 +61,59 @@ struct GemmParams {
   int out_kind;  // 0 = bf16, 1 = fp32, 2 = bf16 hi/lo pair (lo at column + lo_off)
   long long lo_off;
   int act;  // 0 = none, 1 = exact-erf GELU
-  int num_m_blocks, num_n_blocks;
+  int num_m_blocks, num_n_blocks;  // in units of (kCG * 128) x 256 tiles
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) (nn.GELU default, timesformer.py:37).  erf via Abramowitz-Stegun 7.1.26
+// (|abs error| <= 1.5e-7, far below the bf16 / hi-lo rounding of the stored result): one MUFU.RCP + one MUFU.EX2 + 8 FMA.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx(z * z * -1.4426950408889634f);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
+template <int kCG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
+  using C = Cfg<kCG>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -72,19 +121,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const uint32_t sA = base;
   const uint32_t sB = base + STAGES * A_BYTES;
-  float* stg_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES;
-  const uint32_t full_bar = bars;                       // [STAGES]
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  const uint32_t bars = base + STAGES * C::STAGE_BYTES + EPI_WARPS * STG_BYTES;
+  const uint32_t full_bar = bars;                       // [STAGES]   (2-CTA: only the leader's copy is used)
   const uint32_t empty_bar = bars + 8 * STAGES;         // [STAGES]
   const uint32_t tfull_bar = bars + 16 * STAGES;        // [ACC_STAGES]
-  const uint32_t tempty_bar = tfull_bar + 8 * ACC_STAGES;
+  const uint32_t tempty_bar = tfull_bar + 8 * ACC_STAGES;  // (2-CTA: only the leader's copy is used)
   const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 16 * STAGES +
-                                           16 * ACC_STAGES);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -97,20 +146,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, EPI_WARPS);
+      mbar_init(tempty_bar + 8 * a, EPI_WARPS * kCG);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc<1>(tmem_slot, TMEM_COLS);
-    tmem_relinquish<1>();
+    tmem_alloc<kCG>(tmem_slot, TMEM_COLS);
+    tmem_relinquish<kCG>();
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int tile0 = kCG == 2 ? blockIdx.x / 2 : blockIdx.x;
+  const int tile_step = kCG == 2 ? gridDim.x / 2 : gridDim.x;
   const int nk = p.K / BK;
   const int num_iters = p.split ? 3 * nk : nk;
 
@@ -118,9 +169,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // TMA completion bytes of BOTH CTAs are signalled on the leader's `full` barrier
+      const uint32_t full_leader = kCG == 2 ? mapa_u32(full_bar, 0) : full_bar;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / p.num_n_blocks;
         const int n_blk = tile % p.num_n_blocks;
+        const int row_a = (m_blk * kCG + cta_rank) * BM;
+        const int row_b = n_blk * BN + cta_rank * C::B_ROWS;
         for (int it = 0; it < num_iters; ++it) {
           int ka, kb;
           if (p.split) {
@@ -131,19 +186,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ka = kb = it * BK;
           }
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
-          mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
-          tma_load_2d(sA + s * A_BYTES, &tmA, full_bar + 8 * s, ka, m_blk * BM);
-          tma_load_2d(sB + s * B_BYTES, &tmB, full_bar + 8 * s, kb, n_blk * BN);
+          if (kCG == 1) {
+            mbar_arrive_expect_tx(full_bar + 8 * s, C::STAGE_BYTES);
+            tma_load_2d(sA + s * A_BYTES, &tmA, full_bar + 8 * s, ka, row_a);
+            tma_load_2d(sB + s * C::B_BYTES, &tmB, full_bar + 8 * s, kb, row_b);
+          } else {
+            if (leader) mbar_arrive_expect_tx(full_bar + 8 * s, 2 * C::STAGE_BYTES);
+            tma_load_2d_cg2(sA + s * A_BYTES, &tmA, full_leader + 8 * s, ka, row_a);
+            tma_load_2d_cg2(sB + s * C::B_BYTES, &tmB, full_leader + 8 * s, kb, row_b);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM * kCG, BN);
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar + 8 * a, aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + a * BN;
@@ -151,16 +212,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(full_bar + 8 * s, ph);
           tc_fence_after();
           const uint32_t a_addr = sA + s * A_BYTES;
-          const uint32_t b_addr = sB + s * B_BYTES;
+          const uint32_t b_addr = sB + s * C::B_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16<1>(tmem_d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
-                         idesc, (it | k) != 0 ? 1u : 0u);
+            umma_bf16<kCG>(tmem_d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                           idesc, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar + 8 * s);
+          if (kCG == 1) umma_commit(empty_bar + 8 * s); else umma_commit_cg2(empty_bar + 8 * s, 3);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull_bar + 8 * a);
+        if (kCG == 1) umma_commit(tfull_bar + 8 * a); else umma_commit_cg2(tfull_bar + 8 * a, 3);
         if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
       }
     }
@@ -169,26 +230,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const int half = e >> 2;  // which 128-column half of the accumulator
     float* stg = stg_all + e * (32 * STG_STRIDE);
+    const int rrow_l = lane & 7, cg = lane >> 3;  // read-back mapping: 8 rows x 4 column groups of 4 floats
     int a = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile % p.num_n_blocks;
+      const long long row_base = static_cast<long long>(m_blk * kCG + cta_rank) * BM + q * 32;
       mbar_wait(tfull_bar + 8 * a, aph);
       tc_fence_after();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * 128;
+      uint32_t v[32];
+      tmem_ld_32x32(trow, v);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        const int col0 = half * 128 + c * 32;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col0, v);
+        const int gcol0 = n_blk * BN + half * 128 + c * 32;
+        // prefetch the residual values this lane will need at read-back (overlaps the TMEM load and the math)
+        float4 res[8];
+        if (p.residual != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long grow = row_base + (i & 3) * 8 + rrow_l;
+            if (grow < p.M) {
+              const long long rrow = p.res_mod > 0 ? grow % p.res_mod : grow;
+              res[i] = __ldg(reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + gcol0 + 16 * (i >> 2) + cg * 4));
+            }
+          }
+        }
         tmem_ld_wait();
         float f[32];
-        const int gcol0 = n_blk * BN + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (c < 3) tmem_ld_32x32(trow + (c + 1) * 32, v);  // next chunk in flight while this one is processed
         if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + gcol0 + j);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0) + j4);
+            f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
+          }
         }
         if (p.act == 1) {
 #pragma unroll
@@ -204,15 +283,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int row = i * 8 + (lane & 7);
-            const int cg = lane >> 3;
+            const int row = i * 8 + rrow_l;
             float4 val = *reinterpret_cast<const float4*>(stg + row * STG_STRIDE + cg * 4);
-            const long long grow = static_cast<long long>(m_blk) * BM + q * 32 + row;
+            const long long grow = row_base + row;
             const int gcol = gcol0 + 16 * h + cg * 4;
             if (grow < p.M) {
               if (p.residual != nullptr) {
-                const long long rrow = p.res_mod > 0 ? grow % p.res_mod : grow;
-                const float4 r = *reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + gcol);
+                const float4 r = res[h * 4 + i];
                 val.x += r.x; val.y += r.y; val.z += r.z; val.w += r.w;
               }
               if (p.out_kind == 1) {
@@ -236,16 +313,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * a);
+      if (lane == 0) {
+        if (kCG == 1 || leader) mbar_arrive(tempty_bar + 8 * a);
+        else mbar_arrive_cluster(tempty_bar + 8 * a, 0);
+      }
       if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, TMEM_COLS);
+    tmem_dealloc<kCG>(tmem_base, TMEM_COLS);
   }
 }
 
@@ -296,6 +376,53 @@ int num_sms() {
   return n;
 }
 
+static int g_gemm_cta_group = 2;
+void set_gemm_cta_group(int cg) { g_gemm_cta_group = cg == 1 ? 1 : 2; }
+
+template <int kCG>
+static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
+  using C = Cfg<kCG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kCG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const uint64_t kcols = static_cast<uint64_t>(g.K) * (g.split ? 2 : 1);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, kcols, g.lda, BM, BK)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmB, g.W, g.N, kcols, g.ldw, C::B_ROWS, BK)) return rc;
+
+  GemmParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.split = g.split;
+  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.res_mod = g.res_mod;
+  p.out = g.out; p.ldo = g.ldo; p.out_kind = g.out_kind; p.lo_off = g.lo_off; p.act = g.act;
+  p.num_m_blocks = (g.M + BM * kCG - 1) / (BM * kCG);
+  p.num_n_blocks = g.N / BN;
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int max_units = num_sms() / kCG;
+  const int units = tiles < max_units ? tiles : max_units;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * kCG);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfScope prof(PROF_GEMM, 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG>, tmA, tmB, p);
+  if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0) return 0;
   if (g.N % BN != 0) return set_error("gemm: N=%d must be a multiple of %d", g.N, BN);
@@ -304,33 +431,10 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
       (g.ldw % 8))
     return set_error("gemm: operands must be 16-byte aligned with leading dimensions multiple of 8");
   if (g.out_kind < 0 || g.out_kind > 2) return set_error("gemm: bad out_kind %d", g.out_kind);
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-
-  const uint64_t kcols = static_cast<uint64_t>(g.K) * (g.split ? 2 : 1);
-  CUtensorMap tmA, tmB;
-  if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, kcols, g.lda, BM, BK)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tmB, g.W, g.N, kcols, g.ldw, BN, BK)) return rc;
-
-  GemmParams p;
-  p.M = g.M; p.N = g.N; p.K = g.K; p.split = g.split;
-  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.res_mod = g.res_mod;
-  p.out = g.out; p.ldo = g.ldo; p.out_kind = g.out_kind; p.lo_off = g.lo_off; p.act = g.act;
-  p.num_m_blocks = (g.M + BM - 1) / BM;
-  p.num_n_blocks = g.N / BN;
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  ProfScope prof(PROF_GEMM, 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
-  gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
-  count_launch();
-  return 0;
+  // small problems (fewer 256-row tiles than SM pairs would leave half the chip idle) stay on the 1-CTA kernel
+  const long long tiles2 = static_cast<long long>((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
+  if (g_gemm_cta_group == 2 && tiles2 >= num_sms() / 2) return launch_gemm_impl<2>(g, stream);
+  return launch_gemm_impl<1>(g, stream);
 }
 
 }  // namespace dvst

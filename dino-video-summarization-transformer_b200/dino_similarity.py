@@ -127,7 +127,7 @@ class HeadScorer:
     def pair_losses(self, feat_s, feat_t, s_idx, t_idx):
         L = _lib.lib()
         zs, _ = self.head.bottleneck(feat_s)
-        zt, _ = self.head.bottleneck(feat_t)
+        zt = zs if feat_t is feat_s else self.head.bottleneck(feat_t)[0]
         # gather rows per frame (tiny: [F, 256] bf16)
         zs = zs[:, :256].index_select(0, s_idx.long()).contiguous()
         zt = zt[:, :256].index_select(0, t_idx.long()).contiguous()

@@ -42,6 +42,10 @@ const char* dvst_last_error(void);
 long long dvst_launch_count(void);
 int dvst_abi_version(void);
 
+/* Tuning / test hook: 2 (default) lets large GEMMs use tcgen05 cta_group::2 CTA pairs (256x256 tiles); 1 forces the
+ * single-CTA 128x256 kernel. */
+void dvst_set_gemm_cta_group(int cg);
+
 /* Live per-kernel timing for bench.py's roofline: while enabled, every launch is bracketed by CUDA events on its own
  * stream.  dvst_profile_collect waits for the recorded events, sums elapsed ms / work (FLOPs for kind 0 GEMM and
  * 1 attention, bytes for 2 layernorm, 3 elementwise, 4 head-loss) / launch counts per kind, and clears the log. */

@@ -44,6 +44,9 @@ def report(name, got, ref):
 
 torch.manual_seed(0)
 ok = True
+CG = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+L.dvst_set_gemm_cta_group(CG)
+print("cta_group", CG, flush=True)
 
 # 1. identity-weight probe: out[m, n] = A[m, n] for n < K
 M, N, K = 128, 256, 64
@@ -63,7 +66,7 @@ if not report("identity probe 128x256x64", out, ref):
     print("nonzero count", nz.shape[0], "expected", (ref != 0).sum().item())
 
 for (M, N, K) in [(128, 256, 64), (128, 256, 768), (256, 512, 128), (1000, 768, 768), (333, 2304, 768),
-                  (4099, 3072, 768), (4099, 768, 3072)]:
+                  (4099, 3072, 768), (4099, 768, 3072), (40000, 768, 768), (37999, 2304, 768)]:
     A = torch.randn(M, K, device=dev).bfloat16()
     W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     bias = torch.randn(N, device=dev)
