@@ -29,9 +29,8 @@ struct GemmArgs {
   const void* W = nullptr;  // bf16 [N, ldw]  (nn.Linear layout; split: [hi | lo])
   long long ldw = 0;
   const float* bias = nullptr;      // [N] or null
-  const float* residual = nullptr;  // fp32 [M, ldr] or null (may alias out)
+  const float* residual = nullptr;  // null, or == out (fp32): out += result (in-place residual add)
   long long ldr = 0;
-  long long res_mod = 0;            // > 0: residual row = row % res_mod
   void* out = nullptr;
   long long ldo = 0;
   int out_kind = 0;  // 0 bf16, 1 fp32, 2 bf16 hi/lo pair
@@ -54,6 +53,7 @@ int launch_l2norm_rows(const float* in, long long ldi, void* out, long long ldo,
                        float* out_f32, long long M, int cols, cudaStream_t st);
 int launch_colsum(const float* in, long long ldi, float* out, int rows, int cols, cudaStream_t st);
 int launch_center_ema(float* center, const float* batch_sum, float denom, float momentum, int cols, cudaStream_t st);
+int launch_tile_rows768(const float* table, long long period, float* dst, long long rows, cudaStream_t st);
 int launch_broadcast_row768(const float* src, float* dst, long long ldd, int nrows, cudaStream_t st);
 int launch_cls_mean(const float* in, void* out, long long ldo, int split, long long lo_off, long long B, int T,
                     float* out_f32, cudaStream_t st);

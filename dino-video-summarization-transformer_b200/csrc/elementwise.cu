@@ -143,6 +143,17 @@ __global__ void embed_table_kernel(const float* __restrict__ pos, int P, const f
   reinterpret_cast<float4*>(out)[idx] = v;
 }
 
+// dst[r, :] = table[r % period, :]: replicate the [N*T, 768] pos+time table over the batch (the patch-embed GEMM then
+// accumulates onto it with its TMA reduce-add epilogue).
+__global__ void tile_rows768_kernel(const float* __restrict__ table, long long period, float* __restrict__ dst,
+                                    long long rows) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= rows * (D / 4)) return;
+  const long long r = idx / (D / 4);
+  const int c = static_cast<int>(idx % (D / 4));
+  reinterpret_cast<float4*>(dst)[idx] = __ldg(reinterpret_cast<const float4*>(table + (r % period) * D) + c);
+}
+
 // rows[r, :] = src[:] for r in [0, nrows): broadcast of cls_token + pos_embed[0] into the CLS rows (timesformer.py:310).
 __global__ void broadcast_row768_kernel(const float* __restrict__ src, float* __restrict__ dst, long long ldd,
                                         int nrows) {
@@ -325,6 +336,15 @@ int launch_embed_table(const float* pos, int P, const float* time_embed, int T0,
                                                                                N, T);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("embed_table launch failed");
+}
+
+int launch_tile_rows768(const float* table, long long period, float* dst, long long rows, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  const long long total = rows * (D / 4);
+  ProfScope prof(PROF_ELEMENTWISE, static_cast<double>(rows) * D * 4.0, st);
+  tile_rows768_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(table, period, dst, rows);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("tile_rows launch failed");
 }
 
 int launch_broadcast_row768(const float* src, float* dst, long long ldd, int nrows, cudaStream_t st) {

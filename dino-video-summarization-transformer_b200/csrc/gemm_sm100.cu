@@ -12,8 +12,8 @@
 //   warp 0      : TMA producer (one lane)       - ring of {A 128x64, W 256x64 (or its 128-row half)} bf16 tiles
 //   warp 1      : MMA issuer (one lane, leader) - 4 x tcgen05.mma (128|256)x256x16 per stage, tcgen05.commit -> mbarriers
 //   warp 2      : TMEM allocator / deallocator
-//   warps 4..11 : epilogue                      - tcgen05.ld 32x32b.x32 -> bias / GELU -> per-warp smem transpose ->
-//                                                 coalesced residual read + store (fp32, bf16, or bf16 hi/lo pair)
+//   warps 4..11 : epilogue                      - tcgen05.ld 32x32b.x32 -> bias / GELU / dtype -> swizzled smem box ->
+//                                                 TMA store (bf16, fp32, hi/lo pair) or TMA reduce-add (fused residual)
 //
 // `split` mode: A and W hold [hi | lo] bf16 halves along K (lo at column offset K); the K loop then runs the three
 // products hi*hi, hi*lo, lo*hi into the same accumulator (~16 mantissa bits) - the "precision=high" path that
@@ -33,8 +33,9 @@ constexpr int EPI_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int STG_STRIDE = 20;  // fp32 words per staged row (16 payload + 4 pad): conflict-free 128-bit STS/LDS
-constexpr int STG_BYTES = 32 * STG_STRIDE * 4;
+constexpr int STG_BUF_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 B (32 fp32 or 64 bf16 columns), SWIZZLE_128B
+constexpr int STG_BUFS = 2;              // double buffered per epilogue warp
+constexpr int STG_BYTES = STG_BUFS * STG_BUF_BYTES;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 
 // kCG = 1: one CTA per 128x256 tile, each CTA stages the whole 256-row W tile (48 KiB / stage, 4 stages).
@@ -45,7 +46,7 @@ template <int kCG> struct Cfg {
   static constexpr int B_ROWS = BN / kCG;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = kCG == 1 ? 4 : 6;
+  static constexpr int STAGES = kCG == 1 ? 3 : 5;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256;
 };
 
@@ -53,13 +54,9 @@ struct GemmParams {
   int M, N, K;
   int split;
   const float* bias;
-  const float* residual;
-  long long ldr;
-  long long res_mod;  // > 0: residual row = row % res_mod (periodic table)
-  void* out;
-  long long ldo;
-  int out_kind;  // 0 = bf16, 1 = fp32, 2 = bf16 hi/lo pair (lo at column + lo_off)
-  long long lo_off;
+  int accumulate;  // fp32 output only: out += tile (TMA reduce-add in L2) - the fused residual add
+  int out_kind;    // 0 = bf16, 1 = fp32, 2 = bf16 hi/lo pair (lo at column + lo_off)
+  int lo_off;
   int act;  // 0 = none, 1 = exact-erf GELU
   int num_m_blocks, num_n_blocks;  // in units of (kCG * 128) x 256 tiles
 };
@@ -111,7 +108,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 template <int kCG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using C = Cfg<kCG>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -121,7 +118,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const uint32_t sA = base;
   const uint32_t sB = base + STAGES * A_BYTES;
-  float* stg_all = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  const uint32_t stg_all = base + STAGES * C::STAGE_BYTES;  // 1024-byte aligned
   const uint32_t bars = base + STAGES * C::STAGE_BYTES + EPI_WARPS * STG_BYTES;
   const uint32_t full_bar = bars;                       // [STAGES]   (2-CTA: only the leader's copy is used)
   const uint32_t empty_bar = bars + 8 * STAGES;         // [STAGES]
@@ -138,6 +135,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -226,99 +224,136 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= FIRST_EPI_WARP) {
+    // TMEM -> registers -> (bias, GELU, dtype) -> swizzled smem box -> TMA store (or TMA reduce-add for the residual):
+    // each output byte crosses the LSU exactly once (one 128-bit STS); the global write is done by the async proxy.
     const int e = warp - FIRST_EPI_WARP;
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const int half = e >> 2;  // which 128-column half of the accumulator
-    float* stg = stg_all + e * (32 * STG_STRIDE);
-    const int rrow_l = lane & 7, cg = lane >> 3;  // read-back mapping: 8 rows x 4 column groups of 4 floats
+    const uint32_t stg = stg_all + e * STG_BYTES;
+    const uint32_t row_off = lane * 128;
+    const int sw = lane & 7;
+    int buf = 0;
     int a = 0;
     uint32_t aph = 0;
+
+    auto stage_and_store = [&](const uint32_t (&w)[32], int gcol, int grow) {
+      // the TMA store issued STG_BUFS boxes ago must have finished reading this buffer
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(STG_BUFS - 1) : "memory");
+      __syncwarp();
+      const uint32_t dst = stg + buf * STG_BUF_BYTES + row_off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ sw) << 4)), "r"(w[4 * j]),
+                     "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3]) : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t src = stg + buf * STG_BUF_BYTES;
+        if (p.accumulate)
+          asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(src), "r"(gcol), "r"(grow) : "memory");
+        else
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(src), "r"(gcol), "r"(grow) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      buf ^= 1;
+    };
+
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile % p.num_n_blocks;
-      const long long row_base = static_cast<long long>(m_blk * kCG + cta_rank) * BM + q * 32;
+      const int grow = (m_blk * kCG + cta_rank) * BM + q * 32;
       mbar_wait(tfull_bar + 8 * a, aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * 128;
+      const int gcol_base = n_blk * BN + half * 128;
       uint32_t v[32];
       tmem_ld_32x32(trow, v);
+      if (p.out_kind == 1) {
+        // ---- fp32 output: 4 boxes of 32 columns ----
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int gcol0 = n_blk * BN + half * 128 + c * 32;
-        // prefetch the residual values this lane will need at read-back (overlaps the TMEM load and the math)
-        float4 res[8];
-        if (p.residual != nullptr) {
+        for (int c = 0; c < 4; ++c) {
+          const int gcol0 = gcol_base + c * 32;
+          tmem_ld_wait();
+          uint32_t w[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const long long grow = row_base + (i & 3) * 8 + rrow_l;
-            if (grow < p.M) {
-              const long long rrow = p.res_mod > 0 ? grow % p.res_mod : grow;
-              res[i] = __ldg(reinterpret_cast<const float4*>(p.residual + rrow * p.ldr + gcol0 + 16 * (i >> 2) + cg * 4));
+          for (int j = 0; j < 32; ++j) w[j] = v[j];
+          if (c < 3) tmem_ld_32x32(trow + (c + 1) * 32, v);
+          else {  // accumulator fully read: hand the TMEM stage back to the MMA warp before the stores drain
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (kCG == 1 || leader) mbar_arrive(tempty_bar + 8 * a);
+              else mbar_arrive_cluster(tempty_bar + 8 * a, 0);
             }
           }
-        }
-        tmem_ld_wait();
-        float f[32];
+          if (p.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (c < 3) tmem_ld_32x32(trow + (c + 1) * 32, v);  // next chunk in flight while this one is processed
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0) + j4);
-            f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0) + j4);
+              w[4 * j4] = __float_as_uint(__uint_as_float(w[4 * j4]) + b4.x);
+              w[4 * j4 + 1] = __float_as_uint(__uint_as_float(w[4 * j4 + 1]) + b4.y);
+              w[4 * j4 + 2] = __float_as_uint(__uint_as_float(w[4 * j4 + 2]) + b4.z);
+              w[4 * j4 + 3] = __float_as_uint(__uint_as_float(w[4 * j4 + 3]) + b4.w);
+            }
           }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(gelu_erf(__uint_as_float(w[j])));
+          }
+          stage_and_store(w, gcol0, grow);
         }
-        if (p.act == 1) {
+      } else {
+        // ---- bf16 output (optionally hi/lo pair): 2 boxes of 64 columns ----
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int gcol0 = gcol_base + c * 64;
+          uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        }
+          for (int hh = 0; hh < 2; ++hh) {
+            tmem_ld_wait();
+            float f[32];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float4* dst = reinterpret_cast<float4*>(stg + lane * STG_STRIDE);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            dst[j4] = make_float4(f[16 * h + 4 * j4], f[16 * h + 4 * j4 + 1], f[16 * h + 4 * j4 + 2],
-                                  f[16 * h + 4 * j4 + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = i * 8 + rrow_l;
-            float4 val = *reinterpret_cast<const float4*>(stg + row * STG_STRIDE + cg * 4);
-            const long long grow = row_base + row;
-            const int gcol = gcol0 + 16 * h + cg * 4;
-            if (grow < p.M) {
-              if (p.residual != nullptr) {
-                const float4 r = res[h * 4 + i];
-                val.x += r.x; val.y += r.y; val.z += r.z; val.w += r.w;
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (c * 2 + hh < 3) tmem_ld_32x32(trow + (c * 2 + hh + 1) * 32, v);
+            else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (kCG == 1 || leader) mbar_arrive(tempty_bar + 8 * a);
+                else mbar_arrive_cluster(tempty_bar + 8 * a, 0);
               }
-              if (p.out_kind == 1) {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.ldo + gcol) = val;
-              } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldo + gcol;
-                const uint32_t h0 = pack_bf16x2(val.x, val.y), h1 = pack_bf16x2(val.z, val.w);
-                *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
-                if (p.out_kind == 2) {
-                  const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&h0);
-                  const __nv_bfloat162 b1 = *reinterpret_cast<const __nv_bfloat162*>(&h1);
-                  const uint32_t l0 = pack_bf16x2(val.x - __low2float(b0), val.y - __high2float(b0));
-                  const uint32_t l1 = pack_bf16x2(val.z - __low2float(b1), val.w - __high2float(b1));
-                  *reinterpret_cast<uint2*>(o + p.lo_off) = make_uint2(l0, l1);
-                }
+            }
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + hh * 32) + j4);
+                f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t hw = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+              hi[hh * 16 + j] = hw;
+              if (p.out_kind == 2) {
+                const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hw);
+                lo[hh * 16 + j] = pack_bf16x2(f[2 * j] - __low2float(hb), f[2 * j + 1] - __high2float(hb));
               }
             }
           }
-          __syncwarp();
+          stage_and_store(hi, gcol0, grow);
+          if (p.out_kind == 2) stage_and_store(lo, gcol0 + p.lo_off, grow);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kCG == 1 || leader) mbar_arrive(tempty_bar + 8 * a);
-        else mbar_arrive_cluster(tempty_bar + 8 * a, 0);
       }
       if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -351,19 +386,25 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                      uint32_t box_rows, uint32_t box_cols) {
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error("cuTensorMapEncodeTiled entry point not found");
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint64_t gstride[1] = {ld_elems * elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (code %d)", static_cast<int>(r));
   return 0;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(map, ptr, 2, rows, cols, ld_elems, box_rows, box_cols);
 }
 
 int num_sms() {
@@ -390,14 +431,17 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
     attr_set = true;
   }
   const uint64_t kcols = static_cast<uint64_t>(g.K) * (g.split ? 2 : 1);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, kcols, g.lda, BM, BK)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmB, g.W, g.N, kcols, g.ldw, C::B_ROWS, BK)) return rc;
+  const uint64_t out_cols = g.out_kind == 2 ? static_cast<uint64_t>(g.lo_off) + g.N : g.N;
+  if (int rc = make_tmap_2d(&tmO, g.out, g.out_kind == 1 ? 4 : 2, g.M, out_cols, g.ldo, 32, g.out_kind == 1 ? 32 : 64))
+    return rc;
 
   GemmParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.split = g.split;
-  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.res_mod = g.res_mod;
-  p.out = g.out; p.ldo = g.ldo; p.out_kind = g.out_kind; p.lo_off = g.lo_off; p.act = g.act;
+  p.bias = g.bias; p.accumulate = g.residual != nullptr ? 1 : 0;
+  p.out_kind = g.out_kind; p.lo_off = static_cast<int>(g.lo_off); p.act = g.act;
   p.num_m_blocks = (g.M + BM * kCG - 1) / (BM * kCG);
   p.num_n_blocks = g.N / BN;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
@@ -417,7 +461,7 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(PROF_GEMM, 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG>, tmA, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG>, tmA, tmB, tmO, p);
   if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -431,6 +475,10 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
       (g.ldw % 8))
     return set_error("gemm: operands must be 16-byte aligned with leading dimensions multiple of 8");
   if (g.out_kind < 0 || g.out_kind > 2) return set_error("gemm: bad out_kind %d", g.out_kind);
+  if ((reinterpret_cast<uintptr_t>(g.out) & 15) || (g.ldo % (g.out_kind == 1 ? 4 : 8)) || (g.lo_off % 8))
+    return set_error("gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
+  if (g.residual != nullptr && (g.residual != g.out || g.out_kind != 1 || g.ldr != g.ldo))
+    return set_error("gemm: the fused residual add is in place (residual must alias the fp32 output)");
   // small problems (fewer 256-row tiles than SM pairs would leave half the chip idle) stay on the 1-CTA kernel
   const long long tiles2 = static_cast<long long>((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   if (g_gemm_cta_group == 2 && tiles2 >= num_sms() / 2) return launch_gemm_impl<2>(g, stream);

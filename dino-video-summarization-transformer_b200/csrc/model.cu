@@ -206,11 +206,11 @@ static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int
 #define DVST_TRY(expr) do { if ((rc = (expr)) != 0) return rc; } while (0)
 
   auto gemm = [&](const void* A, long long lda_, const void* Wt, const float* bias, long long rows, int Nn, int K,
-                  const float* residual, long long res_mod, void* o, long long ldo, int out_kind, int act) {
+                  const float* residual, void* o, long long ldo, int out_kind, int act) {
     GemmArgs g;
     g.A = A; g.lda = lda_; g.W = Wt; g.ldw = split ? 2LL * K : K; g.bias = bias;
     g.M = static_cast<int>(rows); g.N = Nn; g.K = K; g.split = split;
-    g.residual = residual; g.ldr = D; g.res_mod = res_mod;
+    g.residual = residual; g.ldr = D;
     g.out = o; g.ldo = ldo; g.out_kind = out_kind; g.lo_off = ldo / 2; g.act = act;
     return launch_gemm(g, st);
   };
@@ -221,7 +221,8 @@ static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int
   // ---- patch embedding + positional / temporal embedding (timesformer.py:203-209,287-323) ----
   DVST_TRY(launch_embed_table(m->pos, m->cfg.pos_grid, m->time_embed, m->cfg.num_frames, w.emb, gh, gw, T, st));
   DVST_TRY(launch_im2col16(x_in, w.a, lda, split, D, B, T, H, W, starts, st));
-  DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.emb, N * T, w.x, D, 1, 0));
+  DVST_TRY(launch_tile_rows768(w.emb, N * T, w.x, Mt, st));  // x[b, n, t] = pos + time; the GEMM accumulates onto it
+  DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.x, w.x, D, 1, 0));
   DVST_TRY(launch_broadcast_row768(m->cls_pos0, w.x + Mt * D, D, static_cast<int>(n_cls), st));
 
   for (int i = 0; i < m->cfg.depth; ++i) {
@@ -229,23 +230,23 @@ static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int
     if (att == DVST_ATTN_DIVIDED) {
       // temporal attention over the T tokens of every (b, n); CLS rows excluded (:127-135)
       DVST_TRY(ln(w.x, b.tnorm_w, b.tnorm_b, Mt));
-      DVST_TRY(gemm(w.a, lda, b.tqkv_w, b.tqkv_b, Mt, 3 * D, D, nullptr, 0, w.qkv, ldq, act_kind, 0));
+      DVST_TRY(gemm(w.a, lda, b.tqkv_w, b.tqkv_b, Mt, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
       DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, nullptr, 0, B, T, static_cast<int>(N), Mt, split, st));
       // temporal_fc(proj(.)) folded into one 768x768 GEMM at pack time; residual add fused (:131-135)
-      DVST_TRY(gemm(w.a, lda, b.tproj_w, b.tproj_b, Mt, D, D, w.x, 0, w.x, D, 1, 0));
+      DVST_TRY(gemm(w.a, lda, b.tproj_w, b.tproj_b, Mt, D, D, w.x, w.x, D, 1, 0));
     }
     // spatial (or joint / per-frame) attention (:120-123,140-181)
     DVST_TRY(ln(w.x, b.norm1_w, b.norm1_b, M));
-    DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, 0, w.qkv, ldq, act_kind, 0));
+    DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
     const int mode = att == DVST_ATTN_DIVIDED ? 1 : (att == DVST_ATTN_JOINT ? 2 : 3);
     DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, w.cls_acc, mode, B, T, static_cast<int>(N), Mt, split, st));
     if (att == DVST_ATTN_DIVIDED)
       DVST_TRY(launch_cls_mean(w.cls_acc, static_cast<__nv_bfloat16*>(w.a) + Mt * lda, lda, split, D, B, T, nullptr, st));
-    DVST_TRY(gemm(w.a, lda, b.proj_w, b.proj_b, M, D, D, w.x, 0, w.x, D, 1, 0));
+    DVST_TRY(gemm(w.a, lda, b.proj_w, b.proj_b, M, D, D, w.x, w.x, D, 1, 0));
     // MLP (:184)
     DVST_TRY(ln(w.x, b.norm2_w, b.norm2_b, M));
-    DVST_TRY(gemm(w.a, lda, b.fc1_w, b.fc1_b, M, 4 * D, D, nullptr, 0, w.hid, ldh, act_kind, 1));
-    DVST_TRY(gemm(w.hid, ldh, b.fc2_w, b.fc2_b, M, D, 4 * D, w.x, 0, w.x, D, 1, 0));
+    DVST_TRY(gemm(w.a, lda, b.fc1_w, b.fc1_b, M, 4 * D, D, nullptr, w.hid, ldh, act_kind, 1));
+    DVST_TRY(gemm(w.hid, ldh, b.fc2_w, b.fc2_b, M, D, 4 * D, w.x, w.x, D, 1, 0));
   }
 
   // ---- final norm (:338-345) ----

@@ -113,7 +113,7 @@ for (M, N, K, kind, act, name) in [(200704, 2304, 768, 0, 0, "qkv"), (200704, 76
     W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     bias = torch.randn(N, device=dev)
     res = torch.randn(M, N, device=dev) if kind == 1 else None
-    out = torch.empty(M, N, device=dev, dtype=torch.float32 if kind == 1 else torch.bfloat16)
+    out = res if kind == 1 else torch.empty(M, N, device=dev, dtype=torch.bfloat16)
 
     def run():
         _lib.check(L.dvst_gemm_bf16(_lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(bias), M, N, K, 0, _lib.ptr(res), N,

@@ -9,7 +9,7 @@ for (M, N, K, kind, act, name) in [(200704, 2304, 768, 0, 0, "qkv"), (200704, 76
                                    (200768, 3072, 768, 0, 1, "fc1+gelu"), (200768, 768, 3072, 1, 0, "fc2+res")]:
     A = torch.randn(M, K, device=dev).bfloat16(); W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     bias = torch.randn(N, device=dev); res = torch.randn(M, N, device=dev) if kind == 1 else None
-    out = torch.empty(M, N, device=dev, dtype=torch.float32 if kind == 1 else torch.bfloat16)
+    out = res if kind == 1 else torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
