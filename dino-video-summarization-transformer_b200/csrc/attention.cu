@@ -70,9 +70,149 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// WPP = warps per problem (4: spatial / joint, 1: temporal).  CTA = 4 warps.
-template <int WPP>
-__global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
+// bf16x2 rounding residual of (a, b) given their packed bf16 rounding `hi`
+__device__ __forceinline__ uint32_t pack_lo2(float a, float b, uint32_t hi) {
+  const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hi);
+  return pack2(a - __low2float(hb), b - __high2float(hb));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// One 16-query tile against the S keys staged in shared memory.  K / V rows live at `sK + key * pitch` (128 bytes per
+// row, 16-byte chunks XOR-swizzled with key & 7).  qa = Q A-fragments (4 k-steps).  Leaves the UN-normalised output in
+// o[8][4] and the row sums (quad-reduced) in l0 / l1.
+// SPLIT: q/k/v come as bf16 hi/lo pairs (qb = Q lo fragments, K / V lo rows at sK + lo_delta / sV + lo_delta); every
+// product is evaluated as hi*hi + hi*lo + lo*hi and P is split the same way, ~16 mantissa bits end to end.
+template <bool SPLIT>
+__device__ __forceinline__ void attn_tile(const uint32_t (&qa)[4][4], const uint32_t (&qb)[4][4], uint32_t sK,
+                                          uint32_t sV, uint32_t lo_delta, int pitch, int S, int S_pad, int lane,
+                                          float (&o)[8][4], float& l0, float& l1) {
+  const int tig = lane & 3;
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+  const int n_kblocks = (S + 63) >> 6;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY;
+  l0 = 0.f; l1 = 0.f;
+  const int mat = lane >> 3, r = lane & 7;
+  for (int kb = 0; kb < n_kblocks; ++kb) {
+    const int key0 = kb * 64;
+    const int ntile_pairs = min(4, (S_pad - key0) >> 4);  // 16-key groups present in this block
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+    // ---- S = Q K^T : k-step outer so the 8 accumulator chains are independent ----
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        if (np < ntile_pairs) {
+          const int key = key0 + np * 16 + (mat >> 1) * 8 + r;
+          const int ch = kk * 2 + (mat & 1);
+          uint32_t b0, b1, b2, b3;
+          const uint32_t kaddr = sK + key * pitch + ((ch ^ (key & 7)) << 4);
+          ldsm_x4(kaddr, b0, b1, b2, b3);
+          mma_bf16(s[2 * np], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);
+          mma_bf16(s[2 * np + 1], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b2, b3);
+          if (SPLIT) {
+            mma_bf16(s[2 * np], qb[kk][0], qb[kk][1], qb[kk][2], qb[kk][3], b0, b1);      // q_lo * k_hi
+            mma_bf16(s[2 * np + 1], qb[kk][0], qb[kk][1], qb[kk][2], qb[kk][3], b2, b3);
+            ldsm_x4(kaddr + lo_delta, b0, b1, b2, b3);
+            mma_bf16(s[2 * np], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);      // q_hi * k_lo
+            mma_bf16(s[2 * np + 1], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b2, b3);
+          }
+        }
+      }
+    }
+    // ---- mask + online softmax ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (key0 + 64 > S) {  // only the last key block can hold padded keys
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = key0 + nt * 8 + tig * 2;
+        if (c >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (c + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every block holds >= 1 valid key
+    const float c0 = ex2_approx((m0 - mn0) * scale_log2), c1 = ex2_approx((m1 - mn1) * scale_log2);
+    m0 = mn0; m1 = mn1;
+    const float off0 = mn0 * scale_log2, off1 = mn1 * scale_log2;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2, -off0));
+      s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2, -off0));
+      s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2, -off1));
+      s[nt][3] = ex2_approx(fmaf(s[nt][3], scale_log2, -off1));
+      rs0 += s[nt][0] + s[nt][1];
+      rs1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+    if (kb > 0) {
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (kk < ntile_pairs) {
+        const uint32_t a0 = pack2(s[2 * kk][0], s[2 * kk][1]), a1 = pack2(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t a2 = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (SPLIT) {
+          c0 = pack_lo2(s[2 * kk][0], s[2 * kk][1], a0); c1 = pack_lo2(s[2 * kk][2], s[2 * kk][3], a1);
+          c2 = pack_lo2(s[2 * kk + 1][0], s[2 * kk + 1][1], a2); c3 = pack_lo2(s[2 * kk + 1][2], s[2 * kk + 1][3], a3);
+        }
+        const int key = key0 + kk * 16 + (mat & 1) * 8 + r;
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          const int ch = dp * 2 + (mat >> 1);
+          uint32_t b0, b1, b2, b3;
+          const uint32_t vaddr = sV + key * pitch + ((ch ^ (key & 7)) << 4);
+          ldsm_x4_t(vaddr, b0, b1, b2, b3);
+          mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);
+          mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+          if (SPLIT) {
+            mma_bf16(o[2 * dp], c0, c1, c2, c3, b0, b1);          // p_lo * v_hi
+            mma_bf16(o[2 * dp + 1], c0, c1, c2, c3, b2, b3);
+            ldsm_x4_t(vaddr + lo_delta, b0, b1, b2, b3);
+            mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);          // p_hi * v_lo
+            mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+          }
+        }
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+}
+
+// Generic kernel.  WPP = warps per problem (4: spatial / joint / space-only, 1: long temporal sequences).  CTA = 4 warps.
+// K/V of one (sequence, head) are gathered into shared memory with cp.async (all chunks in flight at once).
+template <int WPP, bool SPLIT>
+__global__ void __launch_bounds__(128, SPLIT ? 2 : (WPP == 4 ? 4 : 3)) attention_kernel(const AttnParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
@@ -85,9 +225,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
   const int seq = active ? static_cast<int>(prob / p.heads) : 0;
   const int head = active ? static_cast<int>(prob % p.heads) : 0;
 
-  uint8_t* sK = smem + static_cast<size_t>(warp / WPP) * (2 * S_pad * 128);
+  constexpr int NBUF = SPLIT ? 4 : 2;  // K, V (and their lo parts)
+  uint8_t* sK = smem + static_cast<size_t>(warp / WPP) * (NBUF * S_pad * 128);
   uint8_t* sV = sK + S_pad * 128;
   const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+  const uint32_t lo_delta = 2 * S_pad * 128;  // K_lo = K + lo_delta, V_lo = V + lo_delta
 
   // ---- stage K and V (16-byte chunks, chunk index XOR (key & 7)) ----
   {
@@ -96,122 +238,64 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     const int total = S_pad * 8;
     for (int idx = tid; idx < total; idx += nthr) {
       const int key = idx >> 3, ch = idx & 7;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      const int off = key * 128 + ((ch ^ (key & 7)) << 4);
       if (active && key < S) {
         const __nv_bfloat16* src = p.qkv + row_of(p, seq, key) * p.ld + head * HD + ch * 8;
-        kv = __ldg(reinterpret_cast<const uint4*>(src + DMODEL));
-        vv = __ldg(reinterpret_cast<const uint4*>(src + 2 * DMODEL));
+        cp_async16(sK_u + off, src + DMODEL);
+        cp_async16(sV_u + off, src + 2 * DMODEL);
+        if (SPLIT) {
+          cp_async16(sK_u + lo_delta + off, src + 3 * DMODEL + DMODEL);
+          cp_async16(sV_u + lo_delta + off, src + 3 * DMODEL + 2 * DMODEL);
+        }
+      } else {
+        *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);
+        if (SPLIT) {
+          *reinterpret_cast<uint4*>(sK + lo_delta + off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sV + lo_delta + off) = make_uint4(0, 0, 0, 0);
+        }
       }
-      const int off = key * 128 + ((ch ^ (key & 7)) << 4);
-      *reinterpret_cast<uint4*>(sK + off) = kv;
-      *reinterpret_cast<uint4*>(sV + off) = vv;
     }
   }
+  const int n_qtiles = S_pad >> 4;
+  // Q fragments straight from global (each row's 64-wide head slice is 128 contiguous bytes); the first tile's loads
+  // are issued before waiting for K/V, later tiles are prefetched one tile ahead.
+  uint32_t qn[4][4], ql[4][4];
+  auto load_q = [&](int qt) {
+    const int r0 = qt * 16 + g, r1 = r0 + 8;
+    const __nv_bfloat16* q0 = p.qkv + row_of(p, seq, r0 < S ? r0 : 0) * p.ld + head * HD;
+    const __nv_bfloat16* q1 = p.qkv + row_of(p, seq, r1 < S ? r1 : 0) * p.ld + head * HD;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int c = kk * 16 + tig * 2;
+      qn[kk][0] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c)) : 0u;
+      qn[kk][1] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c)) : 0u;
+      qn[kk][2] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c + 8)) : 0u;
+      qn[kk][3] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c + 8)) : 0u;
+      if (SPLIT) {
+        ql[kk][0] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + 3 * DMODEL + c)) : 0u;
+        ql[kk][1] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + 3 * DMODEL + c)) : 0u;
+        ql[kk][2] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + 3 * DMODEL + c + 8)) : 0u;
+        ql[kk][3] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + 3 * DMODEL + c + 8)) : 0u;
+      }
+    }
+  };
+  if (active && (warp % WPP) < n_qtiles) load_q(warp % WPP);
+  cp_async_wait_all();
   if (WPP == 1) __syncwarp(); else __syncthreads();
   if (!active) return;
 
-  const float scale_log2 = 0.125f * 1.4426950408889634f;
-  const int n_qtiles = S_pad >> 4;
-  const int n_kblocks = (S + 63) >> 6;
-
   for (int qt = warp % WPP; qt < n_qtiles; qt += WPP) {
     const int r0 = qt * 16 + g, r1 = r0 + 8;
-    // ---- Q fragments straight from global (each row's 64-wide head slice is 128 contiguous bytes) ----
-    uint32_t qa[4][4];
-    {
-      const __nv_bfloat16* q0 = p.qkv + row_of(p, seq, r0 < S ? r0 : 0) * p.ld + head * HD;
-      const __nv_bfloat16* q1 = p.qkv + row_of(p, seq, r1 < S ? r1 : 0) * p.ld + head * HD;
+    uint32_t qa[4][4], qb[4][4];
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int c = kk * 16 + tig * 2;
-        qa[kk][0] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c)) : 0u;
-        qa[kk][1] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c)) : 0u;
-        qa[kk][2] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c + 8)) : 0u;
-        qa[kk][3] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c + 8)) : 0u;
-      }
+    for (int kk = 0; kk < 4; ++kk) {
+      qa[kk][0] = qn[kk][0]; qa[kk][1] = qn[kk][1]; qa[kk][2] = qn[kk][2]; qa[kk][3] = qn[kk][3];
+      if (SPLIT) { qb[kk][0] = ql[kk][0]; qb[kk][1] = ql[kk][1]; qb[kk][2] = ql[kk][2]; qb[kk][3] = ql[kk][3]; }
     }
-    float o[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-
-    for (int kb = 0; kb < n_kblocks; ++kb) {
-      const int key0 = kb * 64;
-      const int ntile_pairs = min(4, (S_pad - key0) >> 4);  // 16-key groups present in this block
-      float s[8][4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-      // ---- S = Q K^T ----
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        if (np < ntile_pairs) {
-          const int mat = lane >> 3, r = lane & 7;
-          const int key = key0 + np * 16 + (mat >> 1) * 8 + r;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int ch = kk * 2 + (mat & 1);
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4(sK_u + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
-            mma_bf16(s[2 * np], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);
-            mma_bf16(s[2 * np + 1], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b2, b3);
-          }
-        }
-      }
-      // ---- mask + online softmax ----
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int c = key0 + nt * 8 + tig * 2;
-        if (c >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-        if (c + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every block holds >= 1 valid key
-      const float c0 = exp2f((m0 - mn0) * scale_log2), c1 = exp2f((m1 - mn1) * scale_log2);
-      m0 = mn0; m1 = mn1;
-      float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = exp2f((s[nt][0] - mn0) * scale_log2);
-        s[nt][1] = exp2f((s[nt][1] - mn0) * scale_log2);
-        s[nt][2] = exp2f((s[nt][2] - mn1) * scale_log2);
-        s[nt][3] = exp2f((s[nt][3] - mn1) * scale_log2);
-        rs0 += s[nt][0] + s[nt][1];
-        rs1 += s[nt][2] + s[nt][3];
-      }
-      l0 = l0 * c0 + rs0;
-      l1 = l1 * c1 + rs1;
-#pragma unroll
-      for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
-      // ---- O += P V ----
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (kk < ntile_pairs) {
-          const uint32_t a0 = pack2(s[2 * kk][0], s[2 * kk][1]), a1 = pack2(s[2 * kk][2], s[2 * kk][3]);
-          const uint32_t a2 = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-          const int mat = lane >> 3, r = lane & 7;
-          const int key = key0 + kk * 16 + (mat & 1) * 8 + r;
-#pragma unroll
-          for (int dp = 0; dp < 4; ++dp) {
-            const int ch = dp * 2 + (mat >> 1);
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4_t(sV_u + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
-            mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);
-            mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
-          }
-        }
-      }
-    }
-    // ---- finalize: quad-reduce the row sums, normalise, store ----
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    if (qt + WPP < n_qtiles) load_q(qt + WPP);
+    float o[8][4], l0, l1;
+    attn_tile<SPLIT>(qa, qb, sK_u, sV_u, lo_delta, 128, S, S_pad, lane, o, l0, l1);
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -243,6 +327,71 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
   }
 }
 
+// Temporal attention for T <= 48: one CTA per (b, n) sequence.  Its T rows of the packed qkv matrix are CONSECUTIVE
+// rows, so the whole [T, 2304] block (all 12 heads, q|k|v) is pulled into shared memory with cp.async in one go
+// (T * 4.5 KiB in flight per CTA, 3 CTAs / SM - enough to run at HBM speed), each of the 4 warps owns 3 heads (Q via
+// ldmatrix), the output tile is
+// written back over the head's own Q slice and the CTA stores the [T, 768] result as fully coalesced 16-byte chunks.
+constexpr int TROW = 3 * DMODEL * 2;  // 4608 bytes per staged row
+__global__ void __launch_bounds__(128, 3) temporal_attention_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const int T = p.S;
+  const int T_pad = (T + 15) & ~15;
+  const int seq = blockIdx.x;
+  const uint32_t sm = smem_u32(smem);
+  const long long row0 = static_cast<long long>(seq) * T;
+
+  // ---- stage the sequence: 288 16-byte chunks per row, chunk c -> segment c/8 (q h0..11 | k h0..11 | v h0..11) ----
+  for (int idx = threadIdx.x; idx < T_pad * 288; idx += 128) {
+    const int row = idx / 288, c = idx - row * 288;
+    const uint32_t off = row * TROW + (c >> 3) * 128 + (((c & 7) ^ (row & 7)) << 4);
+    if (row < T) cp_async16(sm + off, p.qkv + (row0 + row) * p.ld + c * 8);
+    else *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int mat = lane >> 3, r = lane & 7;
+  for (int head = warp; head < 12; head += 4) {  // 4 warps x 3 heads
+  const uint32_t sQ = sm + head * 128, sK = sQ + DMODEL * 2, sV = sQ + 2 * DMODEL * 2;
+  for (int qt = 0; qt < (T_pad >> 4); ++qt) {
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int row = qt * 16 + (mat & 1) * 8 + r;
+      const int ch = kk * 2 + (mat >> 1);
+      ldsm_x4(sQ + row * TROW + ((ch ^ (row & 7)) << 4), qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3]);
+    }
+    float o[8][4], l0, l1;
+    attn_tile<false>(qa, qa, sK, sV, 0, TROW, T, T_pad, lane, o, l0, l1);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    __syncwarp();  // every lane has its Q fragments of this tile: the Q rows may now be overwritten
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int row = qt * 16 + g + half * 8;
+      const float inv = half == 0 ? inv0 : inv1;
+      uint8_t* qrow = smem + row * TROW + head * 128;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const float v0 = o[dt][2 * half] * inv, v1 = o[dt][2 * half + 1] * inv;
+        const uint32_t hi = pack2(v0, v1);
+        const int off = ((dt ^ (row & 7)) << 4) + tig * 4;
+        *reinterpret_cast<uint32_t*>(qrow + off) = hi;
+      }
+    }
+  }
+  }
+  __syncthreads();
+  // ---- coalesced store of the [T, 768] (and optional lo) block ----
+  for (int idx = threadIdx.x; idx < T * 96; idx += 128) {
+    const int row = idx / 96, c = idx - row * 96;
+    const uint4 v = *reinterpret_cast<const uint4*>(smem + row * TROW + (c >> 3) * 128 + (((c & 7) ^ (row & 7)) << 4));
+    *reinterpret_cast<uint4*>(p.out + (row0 + row) * p.ldo + c * 8) = v;
+  }
+}
+
 }  // namespace
 
 int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
@@ -266,28 +415,38 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
   const long long n_prob = static_cast<long long>(p.n_seq) * p.heads;
   cudaError_t e;
   ProfScope prof(PROF_ATTENTION, 4.0 * p.n_seq * p.heads * static_cast<double>(p.S) * p.S * HD, st);
-  if (mode == 0) {
-    const size_t smem = static_cast<size_t>(4) * 2 * S_pad * 128;
-    if (smem > 200 * 1024) return set_error("temporal attention: T=%d too long for the per-warp K/V staging", T);
-    static size_t cur = 0;
-    if (smem > cur) {
-      e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return set_error("attention attr: %s", cudaGetErrorString(e));
-      cur = smem;
-    }
-    attention_kernel<1><<<static_cast<unsigned>((n_prob + 3) / 4), 128, smem, st>>>(p);
-  } else {
-    const size_t smem = static_cast<size_t>(2) * S_pad * 128;
+  auto launch_generic = [&](auto kern, int ppc, size_t smem, size_t* cur) -> int {
     if (smem > 220 * 1024)
-      return set_error("attention: sequence of %d tokens does not fit the shared-memory K/V staging (max 880)", p.S);
-    static size_t cur = 0;
-    if (smem > cur) {
-      e = cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return set_error("attention attr: %s", cudaGetErrorString(e));
-      cur = smem;
+      return set_error("attention: sequence of %d tokens does not fit the shared-memory K/V staging", p.S);
+    if (smem > *cur) {
+      cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (ee != cudaSuccess) return set_error("attention attr: %s", cudaGetErrorString(ee));
+      *cur = smem;
     }
-    attention_kernel<4><<<static_cast<unsigned>(n_prob), 128, smem, st>>>(p);
+    kern<<<static_cast<unsigned>((n_prob + ppc - 1) / ppc), 128, smem, st>>>(p);
+    return 0;
+  };
+  static size_t cur_t = 0, cur1 = 0, cur1s = 0, cur4 = 0, cur4s = 0;
+  const size_t per = static_cast<size_t>(S_pad) * 128;
+  int rc = 0;
+  if (mode == 0 && S_pad <= 48 && !split) {
+    // contiguous-sequence kernel
+    const size_t smem = static_cast<size_t>(S_pad) * TROW;
+    if (smem > cur_t) {
+      e = cudaFuncSetAttribute(temporal_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+      if (e != cudaSuccess) return set_error("attention attr: %s", cudaGetErrorString(e));
+      cur_t = smem;
+    }
+    temporal_attention_kernel<<<static_cast<unsigned>(p.n_seq), 128, smem, st>>>(p);
+  } else if (mode == 0) {
+    rc = split ? launch_generic(attention_kernel<1, true>, 4, 4 * 4 * per, &cur1s)
+               : launch_generic(attention_kernel<1, false>, 4, 4 * 2 * per, &cur1);
+  } else {
+    rc = split ? launch_generic(attention_kernel<4, true>, 1, 4 * per, &cur4s)
+               : launch_generic(attention_kernel<4, false>, 1, 2 * per, &cur4);
   }
+  if (rc != 0) return rc;
   count_launch();
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : set_error("attention launch: %s", cudaGetErrorString(e));

@@ -153,10 +153,22 @@ int dvst_finalize_weights(dvst_model* h) {
   return 0;
 }
 
+// Clips per pass: the batch is walked in chunks of about g_chunk_rows token rows so that the activations of one chunk
+// (x, a, qkv, hid) stay resident in the 126 MB L2 between producer and consumer kernels; 0 = whole batch in one pass.
+static long long g_chunk_rows = 0;
+void dvst_set_chunk_rows(long long rows) { g_chunk_rows = rows < 0 ? 0 : rows; }
+static int chunk_clips(int B, long long rows_per_clip) {
+  if (g_chunk_rows <= 0) return B;
+  long long c = g_chunk_rows / rows_per_clip;
+  if (c < 1) c = 1;
+  return c < B ? static_cast<int>(c) : B;
+}
+
 long long dvst_workspace_bytes(const dvst_model* h, int B, int T, int H, int W) {
   if (h == nullptr || B <= 0 || T <= 0 || H < 16 || W < 16) return -1;
   const Model* m = reinterpret_cast<const Model*>(h);
-  return static_cast<long long>(carve(*m, nullptr, B, T, H / 16, W / 16).total);
+  const int cb = chunk_clips(B, static_cast<long long>(H / 16) * (W / 16) * T);
+  return static_cast<long long>(carve(*m, nullptr, cb, T, H / 16, W / 16).total);
 }
 
 static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
@@ -174,8 +186,29 @@ int dvst_forward_windows(dvst_model* h, const float* frames, int F, const int* s
   return forward_impl(h, frames, starts, n_clips, T, H, W, out, 0, workspace, workspace_bytes, stream);
 }
 
+static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
+                         int get_all, void* workspace, long long workspace_bytes, void* stream);
+
 static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
                         int get_all, void* workspace, long long workspace_bytes, void* stream) {
+  if (h == nullptr) return set_error("dvst_forward_features: null handle");
+  if (B <= 0 || T <= 0 || H < 16 || W < 16) return set_error("dvst_forward_features: bad shape");
+  const Model* m = reinterpret_cast<const Model*>(h);
+  const long long N = static_cast<long long>(H / 16) * (W / 16);
+  const int cb = chunk_clips(B, N * T);
+  const long long out_rows = get_all ? 1 + (m->cfg.attention_type == DVST_ATTN_SPACE_ONLY ? N : N * T) : 1;
+  for (int b0 = 0; b0 < B; b0 += cb) {
+    const int nb = B - b0 < cb ? B - b0 : cb;
+    const float* xin = starts ? x_in : x_in + static_cast<long long>(b0) * 3 * T * H * W;
+    const int rc = forward_chunk(h, xin, starts ? starts + b0 : nullptr, nb, T, H, W, out + b0 * out_rows * D, get_all,
+                                 workspace, workspace_bytes, stream);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
+                         int get_all, void* workspace, long long workspace_bytes, void* stream) {
   if (h == nullptr) return set_error("dvst_forward_features: null handle");
   Model* m = reinterpret_cast<Model*>(h);
   if (!m->finalized) return set_error("dvst_forward_features: weights not finalized");

@@ -46,6 +46,10 @@ int dvst_abi_version(void);
  * single-CTA 128x256 kernel. */
 void dvst_set_gemm_cta_group(int cg);
 
+/* L2-residency tuning: walk a batch in chunks of about `rows` token rows (0 = whole batch per pass).  Results are
+ * bit-identical for any value (rows of every kernel are independent).  Call before dvst_workspace_bytes. */
+void dvst_set_chunk_rows(long long rows);
+
 /* Live per-kernel timing for bench.py's roofline: while enabled, every launch is bracketed by CUDA events on its own
  * stream.  dvst_profile_collect waits for the recorded events, sums elapsed ms / work (FLOPs for kind 0 GEMM and
  * 1 attention, bytes for 2 layernorm, 3 elementwise, 4 head-loss) / launch counts per kind, and clears the log. */

@@ -11,6 +11,8 @@ T = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 depth = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 dev = torch.device("cuda:0")
+if len(sys.argv) > 5:
+    _lib.lib().dvst_set_chunk_rows(int(sys.argv[5]))
 m = VisionTransformer(img_size=224, num_classes=0, depth=depth, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_frames=8)
 m.load_state_dict(synth_backbone_state_dict(0, depth=depth, num_frames=8), strict=True)
 m = m.eval().to(dev)
