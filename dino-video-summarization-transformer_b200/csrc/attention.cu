@@ -5,7 +5,8 @@
 //   TEMPORAL : one sequence per (b, n)  = the T consecutive rows  (b*N + n)*T + t            (:130-131)
 //   SPATIAL  : one sequence per (b, t)  = CLS row (cls_base + b) followed by the N rows (b*N + n)*T + t, i.e. a
 //              stride-T gather; the CLS query's output goes to cls_out[b, t, :] (fp32) for the mean over frames (:140-164)
-//   JOINT    : one sequence per b       = CLS row followed by the N*T rows b*N*T + i          (:120-123)
+//   JOINT    : one sequence per b       = CLS row followed by the N*T rows b*N*T + i          (:120-123); sequences
+//              that do not fit shared memory use the K/V-streaming kernel
 //
 // Flash-style: K/V of one (sequence, head) are staged once in shared memory (XOR-swizzled 16-byte chunks), each warp
 // owns 16-query tiles, scores never leave registers (online softmax over 64-key blocks, exp2 with folded scale).
@@ -87,126 +88,190 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// One 16-query tile against the S keys staged in shared memory.  K / V rows live at `sK + key * pitch` (128 bytes per
-// row, 16-byte chunks XOR-swizzled with key & 7).  qa = Q A-fragments (4 k-steps).  Leaves the UN-normalised output in
-// o[8][4] and the row sums (quad-reduced) in l0 / l1.
-// SPLIT: q/k/v come as bf16 hi/lo pairs (qb = Q lo fragments, K / V lo rows at sK + lo_delta / sV + lo_delta); every
-// product is evaluated as hi*hi + hi*lo + lo*hi and P is split the same way, ~16 mantissa bits end to end.
+// One 64-key block of one 16-query tile.  K / V rows of the block live at `sKb + row * pitch` (row = key - key0, 128
+// bytes per row, 16-byte chunks XOR-swizzled with row & 7).  qa = Q A-fragments (4 k-steps).  Carries the online-softmax
+// state (m, l un-reduced over the quad, un-normalised o).
+// SPLIT: q/k/v come as bf16 hi/lo pairs (qb = Q lo fragments, K / V lo rows at + lo_delta); every product is evaluated
+// as hi*hi + hi*lo + lo*hi and P is split the same way, ~16 mantissa bits end to end.
+template <bool SPLIT>
+__device__ __forceinline__ void attn_block(const uint32_t (&qa)[4][4], const uint32_t (&qb)[4][4], uint32_t sKb,
+                                           uint32_t sVb, uint32_t lo_delta, int pitch, int key0, int S,
+                                           int ntile_pairs, bool first, int lane, float (&o)[8][4], float& m0,
+                                           float& m1, float& l0, float& l1) {
+  const int tig = lane & 3;
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+  const int mat = lane >> 3, r = lane & 7;
+  float s[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+  // ---- S = Q K^T : k-step outer so the 8 accumulator chains are independent ----
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      if (np < ntile_pairs) {
+        const int row = np * 16 + (mat >> 1) * 8 + r;
+        const int ch = kk * 2 + (mat & 1);
+        uint32_t b0, b1, b2, b3;
+        const uint32_t kaddr = sKb + row * pitch + ((ch ^ (row & 7)) << 4);
+        ldsm_x4(kaddr, b0, b1, b2, b3);
+        mma_bf16(s[2 * np], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);
+        mma_bf16(s[2 * np + 1], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b2, b3);
+        if (SPLIT) {
+          mma_bf16(s[2 * np], qb[kk][0], qb[kk][1], qb[kk][2], qb[kk][3], b0, b1);      // q_lo * k_hi
+          mma_bf16(s[2 * np + 1], qb[kk][0], qb[kk][1], qb[kk][2], qb[kk][3], b2, b3);
+          ldsm_x4(kaddr + lo_delta, b0, b1, b2, b3);
+          mma_bf16(s[2 * np], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);      // q_hi * k_lo
+          mma_bf16(s[2 * np + 1], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b2, b3);
+        }
+      }
+    }
+  }
+  // ---- mask + online softmax ----
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  if (key0 + 64 > S) {  // only the last key block can hold padded keys
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = key0 + nt * 8 + tig * 2;
+      if (c >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (c + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every block holds >= 1 valid key
+  const float c0 = ex2_approx((m0 - mn0) * scale_log2), c1 = ex2_approx((m1 - mn1) * scale_log2);
+  m0 = mn0; m1 = mn1;
+  const float off0 = mn0 * scale_log2, off1 = mn1 * scale_log2;
+  float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2, -off0));
+    s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2, -off0));
+    s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2, -off1));
+    s[nt][3] = ex2_approx(fmaf(s[nt][3], scale_log2, -off1));
+    rs0 += s[nt][0] + s[nt][1];
+    rs1 += s[nt][2] + s[nt][3];
+  }
+  l0 = l0 * c0 + rs0;
+  l1 = l1 * c1 + rs1;
+  if (!first) {
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
+  }
+  // ---- O += P V ----
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    if (kk < ntile_pairs) {
+      const uint32_t a0 = pack2(s[2 * kk][0], s[2 * kk][1]), a1 = pack2(s[2 * kk][2], s[2 * kk][3]);
+      const uint32_t a2 = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+      if (SPLIT) {
+        e0 = pack_lo2(s[2 * kk][0], s[2 * kk][1], a0); e1 = pack_lo2(s[2 * kk][2], s[2 * kk][3], a1);
+        e2 = pack_lo2(s[2 * kk + 1][0], s[2 * kk + 1][1], a2); e3 = pack_lo2(s[2 * kk + 1][2], s[2 * kk + 1][3], a3);
+      }
+      const int row = kk * 16 + (mat & 1) * 8 + r;
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        const int ch = dp * 2 + (mat >> 1);
+        uint32_t b0, b1, b2, b3;
+        const uint32_t vaddr = sVb + row * pitch + ((ch ^ (row & 7)) << 4);
+        ldsm_x4_t(vaddr, b0, b1, b2, b3);
+        mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);
+        mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+        if (SPLIT) {
+          mma_bf16(o[2 * dp], e0, e1, e2, e3, b0, b1);          // p_lo * v_hi
+          mma_bf16(o[2 * dp + 1], e0, e1, e2, e3, b2, b3);
+          ldsm_x4_t(vaddr + lo_delta, b0, b1, b2, b3);
+          mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);          // p_hi * v_lo
+          mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+    }
+  }
+}
+
+// One 16-query tile against all S keys staged in shared memory (rows at sK + key * pitch).  Leaves the UN-normalised
+// output in o[8][4] and the quad-reduced row sums in l0 / l1.
 template <bool SPLIT>
 __device__ __forceinline__ void attn_tile(const uint32_t (&qa)[4][4], const uint32_t (&qb)[4][4], uint32_t sK,
                                           uint32_t sV, uint32_t lo_delta, int pitch, int S, int S_pad, int lane,
                                           float (&o)[8][4], float& l0, float& l1) {
-  const int tig = lane & 3;
-  const float scale_log2 = 0.125f * 1.4426950408889634f;
-  const int n_kblocks = (S + 63) >> 6;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY;
   l0 = 0.f; l1 = 0.f;
-  const int mat = lane >> 3, r = lane & 7;
+  const int n_kblocks = (S + 63) >> 6;
   for (int kb = 0; kb < n_kblocks; ++kb) {
     const int key0 = kb * 64;
-    const int ntile_pairs = min(4, (S_pad - key0) >> 4);  // 16-key groups present in this block
-    float s[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-    // ---- S = Q K^T : k-step outer so the 8 accumulator chains are independent ----
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        if (np < ntile_pairs) {
-          const int key = key0 + np * 16 + (mat >> 1) * 8 + r;
-          const int ch = kk * 2 + (mat & 1);
-          uint32_t b0, b1, b2, b3;
-          const uint32_t kaddr = sK + key * pitch + ((ch ^ (key & 7)) << 4);
-          ldsm_x4(kaddr, b0, b1, b2, b3);
-          mma_bf16(s[2 * np], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);
-          mma_bf16(s[2 * np + 1], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b2, b3);
-          if (SPLIT) {
-            mma_bf16(s[2 * np], qb[kk][0], qb[kk][1], qb[kk][2], qb[kk][3], b0, b1);      // q_lo * k_hi
-            mma_bf16(s[2 * np + 1], qb[kk][0], qb[kk][1], qb[kk][2], qb[kk][3], b2, b3);
-            ldsm_x4(kaddr + lo_delta, b0, b1, b2, b3);
-            mma_bf16(s[2 * np], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);      // q_hi * k_lo
-            mma_bf16(s[2 * np + 1], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b2, b3);
-          }
-        }
-      }
-    }
-    // ---- mask + online softmax ----
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-    if (key0 + 64 > S) {  // only the last key block can hold padded keys
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int c = key0 + nt * 8 + tig * 2;
-        if (c >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-        if (c + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-      }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every block holds >= 1 valid key
-    const float c0 = ex2_approx((m0 - mn0) * scale_log2), c1 = ex2_approx((m1 - mn1) * scale_log2);
-    m0 = mn0; m1 = mn1;
-    const float off0 = mn0 * scale_log2, off1 = mn1 * scale_log2;
-    float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2, -off0));
-      s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2, -off0));
-      s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2, -off1));
-      s[nt][3] = ex2_approx(fmaf(s[nt][3], scale_log2, -off1));
-      rs0 += s[nt][0] + s[nt][1];
-      rs1 += s[nt][2] + s[nt][3];
-    }
-    l0 = l0 * c0 + rs0;
-    l1 = l1 * c1 + rs1;
-    if (kb > 0) {
-#pragma unroll
-      for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
-    }
-    // ---- O += P V ----
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      if (kk < ntile_pairs) {
-        const uint32_t a0 = pack2(s[2 * kk][0], s[2 * kk][1]), a1 = pack2(s[2 * kk][2], s[2 * kk][3]);
-        const uint32_t a2 = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (SPLIT) {
-          c0 = pack_lo2(s[2 * kk][0], s[2 * kk][1], a0); c1 = pack_lo2(s[2 * kk][2], s[2 * kk][3], a1);
-          c2 = pack_lo2(s[2 * kk + 1][0], s[2 * kk + 1][1], a2); c3 = pack_lo2(s[2 * kk + 1][2], s[2 * kk + 1][3], a3);
-        }
-        const int key = key0 + kk * 16 + (mat & 1) * 8 + r;
-#pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {
-          const int ch = dp * 2 + (mat >> 1);
-          uint32_t b0, b1, b2, b3;
-          const uint32_t vaddr = sV + key * pitch + ((ch ^ (key & 7)) << 4);
-          ldsm_x4_t(vaddr, b0, b1, b2, b3);
-          mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);
-          mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
-          if (SPLIT) {
-            mma_bf16(o[2 * dp], c0, c1, c2, c3, b0, b1);          // p_lo * v_hi
-            mma_bf16(o[2 * dp + 1], c0, c1, c2, c3, b2, b3);
-            ldsm_x4_t(vaddr + lo_delta, b0, b1, b2, b3);
-            mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);          // p_hi * v_lo
-            mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
-          }
-        }
-      }
-    }
+    attn_block<SPLIT>(qa, qb, sK + key0 * pitch, sV + key0 * pitch, lo_delta, pitch, key0, S,
+                      min(4, (S_pad - key0) >> 4), kb == 0, lane, o, m0, m1, l0, l1);
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+}
+
+// Normalise and store one 16-row output tile (rows r0 = tile*16 + lane/4 and r0 + 8 of sequence `seq`).
+__device__ __forceinline__ void store_tile(const AttnParams& p, int seq, int head, int r0, const float (&o)[8][4],
+                                           float l0, float l1, int lane) {
+  const int tig = lane & 3;
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int r = r0 + half * 8;
+    if (r >= p.S) continue;
+    const float inv = half == 0 ? inv0 : inv1;
+    if (p.mode == 1 && r == 0) {
+      const int b = seq / p.T, t = seq - b * p.T;
+      float* dst = p.cls_out + (static_cast<long long>(b) * p.T + t) * DMODEL + head * HD;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt)
+        *reinterpret_cast<float2*>(dst + dt * 8 + tig * 2) = make_float2(o[dt][2 * half] * inv, o[dt][2 * half + 1] * inv);
+    } else {
+      __nv_bfloat16* dst = p.out + row_of(p, seq, r) * p.ldo + head * HD;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const float v0 = o[dt][2 * half] * inv, v1 = o[dt][2 * half + 1] * inv;
+        const uint32_t hi = pack2(v0, v1);
+        *reinterpret_cast<uint32_t*>(dst + dt * 8 + tig * 2) = hi;
+        if (p.split) *reinterpret_cast<uint32_t*>(dst + p.lo_off + dt * 8 + tig * 2) = pack_lo2(v0, v1, hi);
+      }
+    }
+  }
+}
+
+// Q A-fragments of the 16-row tile starting at row r_base, straight from global (each row's 64-wide head slice is 128
+// contiguous bytes).
+template <bool SPLIT>
+__device__ __forceinline__ void load_q_frags(const AttnParams& p, int seq, int head, int r_base, int lane,
+                                             uint32_t (&qh)[4][4], uint32_t (&ql)[4][4]) {
+  const int g = lane >> 2, tig = lane & 3;
+  const int r0 = r_base + g, r1 = r0 + 8, S = p.S;
+  const __nv_bfloat16* q0 = p.qkv + row_of(p, seq, r0 < S ? r0 : 0) * p.ld + head * HD;
+  const __nv_bfloat16* q1 = p.qkv + row_of(p, seq, r1 < S ? r1 : 0) * p.ld + head * HD;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const int c = kk * 16 + tig * 2;
+    qh[kk][0] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c)) : 0u;
+    qh[kk][1] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c)) : 0u;
+    qh[kk][2] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c + 8)) : 0u;
+    qh[kk][3] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c + 8)) : 0u;
+    if (SPLIT) {
+      ql[kk][0] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + 3 * DMODEL + c)) : 0u;
+      ql[kk][1] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + 3 * DMODEL + c)) : 0u;
+      ql[kk][2] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + 3 * DMODEL + c + 8)) : 0u;
+      ql[kk][3] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + 3 * DMODEL + c + 8)) : 0u;
+    }
+  }
 }
 
 // Generic kernel.  WPP = warps per problem (4: spatial / joint / space-only, 1: long temporal sequences).  CTA = 4 warps.
@@ -258,73 +323,100 @@ __global__ void __launch_bounds__(128, SPLIT ? 2 : (WPP == 4 ? 4 : 3)) attention
     }
   }
   const int n_qtiles = S_pad >> 4;
-  // Q fragments straight from global (each row's 64-wide head slice is 128 contiguous bytes); the first tile's loads
-  // are issued before waiting for K/V, later tiles are prefetched one tile ahead.
+  // the first tile's Q loads are issued before waiting for K/V, later tiles are prefetched one tile ahead
   uint32_t qn[4][4], ql[4][4];
-  auto load_q = [&](int qt) {
-    const int r0 = qt * 16 + g, r1 = r0 + 8;
-    const __nv_bfloat16* q0 = p.qkv + row_of(p, seq, r0 < S ? r0 : 0) * p.ld + head * HD;
-    const __nv_bfloat16* q1 = p.qkv + row_of(p, seq, r1 < S ? r1 : 0) * p.ld + head * HD;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int c = kk * 16 + tig * 2;
-      qn[kk][0] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c)) : 0u;
-      qn[kk][1] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c)) : 0u;
-      qn[kk][2] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + c + 8)) : 0u;
-      qn[kk][3] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + c + 8)) : 0u;
-      if (SPLIT) {
-        ql[kk][0] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + 3 * DMODEL + c)) : 0u;
-        ql[kk][1] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + 3 * DMODEL + c)) : 0u;
-        ql[kk][2] = r0 < S ? __ldg(reinterpret_cast<const uint32_t*>(q0 + 3 * DMODEL + c + 8)) : 0u;
-        ql[kk][3] = r1 < S ? __ldg(reinterpret_cast<const uint32_t*>(q1 + 3 * DMODEL + c + 8)) : 0u;
-      }
-    }
-  };
-  if (active && (warp % WPP) < n_qtiles) load_q(warp % WPP);
+  if (active && (warp % WPP) < n_qtiles) load_q_frags<SPLIT>(p, seq, head, (warp % WPP) * 16, lane, qn, ql);
   cp_async_wait_all();
   if (WPP == 1) __syncwarp(); else __syncthreads();
   if (!active) return;
 
   for (int qt = warp % WPP; qt < n_qtiles; qt += WPP) {
-    const int r0 = qt * 16 + g, r1 = r0 + 8;
     uint32_t qa[4][4], qb[4][4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       qa[kk][0] = qn[kk][0]; qa[kk][1] = qn[kk][1]; qa[kk][2] = qn[kk][2]; qa[kk][3] = qn[kk][3];
       if (SPLIT) { qb[kk][0] = ql[kk][0]; qb[kk][1] = ql[kk][1]; qb[kk][2] = ql[kk][2]; qb[kk][3] = ql[kk][3]; }
     }
-    if (qt + WPP < n_qtiles) load_q(qt + WPP);
+    if (qt + WPP < n_qtiles) load_q_frags<SPLIT>(p, seq, head, (qt + WPP) * 16, lane, qn, ql);
     float o[8][4], l0, l1;
     attn_tile<SPLIT>(qa, qb, sK_u, sV_u, lo_delta, 128, S, S_pad, lane, o, l0, l1);
-    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int r = half == 0 ? r0 : r1;
-      if (r >= S) continue;
-      const float inv = half == 0 ? inv0 : inv1;
-      if (p.mode == 1 && r == 0) {
-        const int b = seq / p.T, t = seq - b * p.T;
-        float* dst = p.cls_out + (static_cast<long long>(b) * p.T + t) * DMODEL + head * HD;
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt)
-          *reinterpret_cast<float2*>(dst + dt * 8 + tig * 2) =
-              make_float2(o[dt][2 * half] * inv, o[dt][2 * half + 1] * inv);
+    store_tile(p, seq, head, qt * 16 + g, o, l0, l1, lane);
+  }
+}
+
+// Long sequences (joint space-time attention, 1 + N*T tokens - 6 273 at T = 32): one CTA per (sequence, head, block of
+// 64 queries); K / V are streamed through a double-buffered cp.async ring in 64-key chunks (re-read from L2 by every
+// query block), the online-softmax state stays in registers.
+template <bool SPLIT>
+__global__ void __launch_bounds__(128, SPLIT ? 2 : 3) attention_stream_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2;
+  const int S = p.S;
+  const int seq = blockIdx.y / p.heads, head = blockIdx.y % p.heads;
+  const int q_base = blockIdx.x * 64 + warp * 16;
+  constexpr int NBUF = SPLIT ? 4 : 2;
+  constexpr int STAGE = NBUF * 64 * 128;          // K | V (| K_lo | V_lo), 64 rows of 128 B each
+  constexpr uint32_t lo_delta = 2 * 64 * 128;
+  const uint32_t sm = smem_u32(smem);
+  const int n_kb = (S + 63) >> 6;
+
+  auto prefetch = [&](int kb) {
+    const uint32_t base = sm + (kb & 1) * STAGE;
+    uint8_t* basep = smem + (kb & 1) * STAGE;
+    for (int idx = threadIdx.x; idx < 64 * 8; idx += 128) {
+      const int row = idx >> 3, ch = idx & 7;
+      const int key = kb * 64 + row;
+      const int off = row * 128 + ((ch ^ (row & 7)) << 4);
+      if (key < S) {
+        const __nv_bfloat16* src = p.qkv + row_of(p, seq, key) * p.ld + head * HD + ch * 8;
+        cp_async16(base + off, src + DMODEL);
+        cp_async16(base + 64 * 128 + off, src + 2 * DMODEL);
+        if (SPLIT) {
+          cp_async16(base + lo_delta + off, src + 3 * DMODEL + DMODEL);
+          cp_async16(base + lo_delta + 64 * 128 + off, src + 3 * DMODEL + 2 * DMODEL);
+        }
       } else {
-        __nv_bfloat16* dst = p.out + row_of(p, seq, r) * p.ldo + head * HD;
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt) {
-          const float v0 = o[dt][2 * half] * inv, v1 = o[dt][2 * half + 1] * inv;
-          const uint32_t hi = pack2(v0, v1);
-          *reinterpret_cast<uint32_t*>(dst + dt * 8 + tig * 2) = hi;
-          if (p.split) {
-            const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hi);
-            *reinterpret_cast<uint32_t*>(dst + p.lo_off + dt * 8 + tig * 2) =
-                pack2(v0 - __low2float(hb), v1 - __high2float(hb));
-          }
+        *reinterpret_cast<uint4*>(basep + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(basep + 64 * 128 + off) = make_uint4(0, 0, 0, 0);
+        if (SPLIT) {
+          *reinterpret_cast<uint4*>(basep + lo_delta + off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(basep + lo_delta + 64 * 128 + off) = make_uint4(0, 0, 0, 0);
         }
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  prefetch(0);
+  uint32_t qa[4][4], qb[4][4];
+  load_q_frags<SPLIT>(p, seq, head, q_base, lane, qa, qb);
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int S_pad = (S + 15) & ~15;
+  for (int kb = 0; kb < n_kb; ++kb) {
+    if (kb + 1 < n_kb) {
+      prefetch(kb + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (q_base < S) {
+      const uint32_t base = sm + (kb & 1) * STAGE;
+      attn_block<SPLIT>(qa, qb, base, base + 64 * 128, lo_delta, 128, kb * 64, S, min(4, (S_pad - kb * 64) >> 4), kb == 0,
+                        lane, o, m0, m1, l0, l1);
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled two iterations later
   }
+  if (q_base >= S) return;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  store_tile(p, seq, head, q_base + g, o, l0, l1, lane);
 }
 
 // Temporal attention for T <= 48: one CTA per (b, n) sequence.  Its T rows of the packed qkv matrix are CONSECUTIVE
@@ -442,6 +534,17 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
   } else if (mode == 0) {
     rc = split ? launch_generic(attention_kernel<1, true>, 4, 4 * 4 * per, &cur1s)
                : launch_generic(attention_kernel<1, false>, 4, 4 * 2 * per, &cur1);
+  } else if ((split ? 4 : 2) * per > 200 * 1024) {
+    // long sequence: K/V streamed in 64-key chunks, one CTA per 64-query block
+    dim3 grid(static_cast<unsigned>((p.S + 63) / 64), static_cast<unsigned>(n_prob));
+    if (n_prob > 65535) return set_error("attention: too many (sequence, head) problems for the streaming kernel");
+    if (split) {
+      static bool set = false;
+      if (!set) { cudaFuncSetAttribute(attention_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 64 * 128); set = true; }
+      attention_stream_kernel<true><<<grid, 128, 2 * 4 * 64 * 128, st>>>(p);
+    } else {
+      attention_stream_kernel<false><<<grid, 128, 2 * 2 * 64 * 128, st>>>(p);
+    }
   } else {
     rc = split ? launch_generic(attention_kernel<4, true>, 1, 4 * per, &cur4s)
                : launch_generic(attention_kernel<4, false>, 1, 2 * per, &cur4);

@@ -97,7 +97,8 @@ def _attn_ref(q, k, v):
 
 
 @pytest.mark.parametrize("mode,B,T,N", [(0, 2, 16, 9), (0, 1, 3, 5), (0, 1, 30, 4), (0, 1, 60, 2), (0, 1, 1, 3),
-                                        (1, 2, 3, 196), (1, 1, 2, 36), (2, 2, 2, 196), (3, 2, 2, 196)])
+                                        (1, 2, 3, 196), (1, 1, 2, 36), (2, 2, 2, 196), (3, 2, 2, 196),
+                                        (2, 1, 5, 196), (2, 1, 32, 196)])
 def test_attention_modes(dev, mode, B, T, N):
     torch.manual_seed(mode * 100 + T)
     L = _lib.lib()

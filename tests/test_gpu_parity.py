@@ -64,7 +64,7 @@ def test_backbone_vs_reference_golden(dev, name, prec):
     with torch.no_grad():
         f = m(x)
     assert tuple(f.shape) == (c["B"], 768) and f.dtype == torch.float32
-    assert _rel(f, c["feat"]) < (FEAT_TOL if prec == "bf16" else 5e-3)
+    assert _rel(f, c["feat"]) < (FEAT_TOL if prec == "bf16" else 1e-4)
 
 
 def test_get_all_token_order_vs_oracle(dev):
@@ -118,14 +118,15 @@ def test_config1_end_to_end(dev):
     head = DINOHead(768, 65536)
     head.load_state_dict(synth_head_state_dict(2), strict=True)
     head = head.to(dev).eval()
-    for prec, tol_r in (("bf16", 5e-2), ("high", 1e-2)):
+    for prec, tol_r in (("bf16", 5e-2), ("high", LOSS_TOL)):
         m = build(dev, 0, 12, prec=prec)
         with torch.no_grad():
             fs, ft = m(xs), m(xt)
         assert _rel(fs, G["feat_s"]) < FEAT_TOL and _rel(ft, G["feat_t"]) < FEAT_TOL
         # mode H (north-star contract): loss within 1e-3
         assert _relmax(HeadScorer(head, 0.04, 0.1).pair_losses(fs, ft, idx, idx), G["loss_H65536_0.04_0.1_zero"]) < LOSS_TOL
-        # mode R (tau_t = 0.02 amplifies feature error 50x; SURVEY finding 3): measured tolerance, stated here
+        # mode R (tau_t = 0.02 amplifies feature error 50x; SURVEY finding 3): bf16 operands cannot meet 1e-3 (stated,
+        # measured ~2e-2); precision="high" (2-term bf16 split in every GEMM and both attentions) does
         assert _relmax(DINOLoss(768, 0.02, 0.3).to(dev).pair_losses(fs, ft), G["loss_R"]) < tol_r
 
 
@@ -140,7 +141,7 @@ def test_driver_golden_and_invariants(dev):
         ref = D["loss"][name]
         assert len(got) == len(ref)
         assert got[0] == got[1] and got[-1] == got[-2]
-        assert _relmax(got, ref) < 1e-2
+        assert _relmax(got, ref) < LOSS_TOL  # reference-exact mode R through the reference's own driver loop
 
 
 def test_dummy_video_path(dev):
