@@ -74,16 +74,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(z * z * -1.4426950408889634f);
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  // With q = 0.5 (1 - erf(|x| / sqrt 2)) = 0.5 t P(t) exp(-x^2 / 2), t = 1 / (1 + 0.3275911 |x| / sqrt 2):
+  //   x >= 0: x Phi(x) = x - x q,   x < 0: x Phi(x) = x q = -|x| q   =>   GELU(x) = max(x, 0) - |x| q.
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float e = ex2_approx((x * -0.72134752044448170368f) * x);  // exp(-x^2 / 2)
+  const float q = (p * t) * e;
+  return fmaf(-ax, q, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -105,7 +106,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   return r;
 }
 
-template <int kCG>
+// kOut: 0 = bf16, 1 = fp32 (plain or reduce-add), 2 = bf16 hi/lo pair.  kAct: 0 = none, 1 = exact-erf GELU.  Compile-time
+// so the epilogue (issue-bound next to the 256x256x768 MMA of fc1) carries no predicated code of the other modes.
+template <int kCG, int kOut, int kAct>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
@@ -268,9 +271,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * 128;
       const int gcol_base = n_blk * BN + half * 128;
-      uint32_t v[32];
+      uint32_t v[32], v2[32];
       tmem_ld_32x32(trow, v);
-      if (p.out_kind == 1) {
+      if constexpr (kOut == 1) {
         // ---- fp32 output: 4 boxes of 32 columns ----
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -298,25 +301,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               w[4 * j4 + 3] = __float_as_uint(__uint_as_float(w[4 * j4 + 3]) + b4.w);
             }
           }
-          if (p.act == 1) {
+          if constexpr (kAct == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(gelu_erf(__uint_as_float(w[j])));
           }
           stage_and_store(w, gcol0, grow);
         }
       } else {
-        // ---- bf16 output (optionally hi/lo pair): 2 boxes of 64 columns ----
+        // ---- bf16 output (optionally hi/lo pair): 2 boxes of 64 columns; the two 32-column register sets ping-pong so
+        // the next tcgen05.ld is in flight while the current set goes through bias / GELU / pack ----
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           const int gcol0 = gcol_base + c * 64;
           uint32_t hi[32], lo[32];
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
+            uint32_t (&cur)[32] = hh == 0 ? v : v2;
+            uint32_t (&nxt)[32] = hh == 0 ? v2 : v;
             tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (c * 2 + hh < 3) tmem_ld_32x32(trow + (c * 2 + hh + 1) * 32, v);
+            if (c * 2 + hh < 3) tmem_ld_32x32(trow + (c * 2 + hh + 1) * 32, nxt);
             else {
               tc_fence_before();
               __syncwarp();
@@ -325,14 +328,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 else mbar_arrive_cluster(tempty_bar + 8 * a, 0);
               }
             }
-            if (p.bias != nullptr) {
+            float f[32];
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + hh * 32) + j4);
-                f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
-              }
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(cur[j]);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {  // branch-free: a null bias adds zeros
+              const float4 b4 = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + hh * 32) + j4)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+              f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
             }
-            if (p.act == 1) {
+            if constexpr (kAct == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
             }
@@ -340,14 +345,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 16; ++j) {
               const uint32_t hw = pack_bf16x2(f[2 * j], f[2 * j + 1]);
               hi[hh * 16 + j] = hw;
-              if (p.out_kind == 2) {
+              if constexpr (kOut == 2) {
                 const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hw);
                 lo[hh * 16 + j] = pack_bf16x2(f[2 * j] - __low2float(hb), f[2 * j + 1] - __high2float(hb));
               }
             }
           }
           stage_and_store(hi, gcol0, grow);
-          if (p.out_kind == 2) stage_and_store(lo, gcol0 + p.lo_off, grow);
+          if constexpr (kOut == 2) stage_and_store(lo, gcol0 + p.lo_off, grow);
         }
       }
       if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
@@ -420,12 +425,12 @@ int num_sms() {
 static int g_gemm_cta_group = 2;
 void set_gemm_cta_group(int cg) { g_gemm_cta_group = cg == 1 ? 1 : 2; }
 
-template <int kCG>
+template <int kCG, int kOut, int kAct>
 static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   using C = Cfg<kCG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kCG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kCG, kOut, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -461,7 +466,7 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(PROF_GEMM, 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG>, tmA, tmB, tmO, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG, kOut, kAct>, tmA, tmB, tmO, p);
   if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -481,8 +486,19 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     return set_error("gemm: the fused residual add is in place (residual must alias the fp32 output)");
   // small problems (fewer 256-row tiles than SM pairs would leave half the chip idle) stay on the 1-CTA kernel
   const long long tiles2 = static_cast<long long>((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
-  if (g_gemm_cta_group == 2 && tiles2 >= num_sms() / 2) return launch_gemm_impl<2>(g, stream);
-  return launch_gemm_impl<1>(g, stream);
+  if (g.act < 0 || g.act > 1) return set_error("gemm: bad act %d", g.act);
+  const bool cg2 = g_gemm_cta_group == 2 && tiles2 >= num_sms() / 2;
+#define DVST_GEMM_CASE(OUT, ACT)                                                                   \
+  if (g.out_kind == OUT && g.act == ACT)                                                           \
+    return cg2 ? launch_gemm_impl<2, OUT, ACT>(g, stream) : launch_gemm_impl<1, OUT, ACT>(g, stream);
+  DVST_GEMM_CASE(0, 0)
+  DVST_GEMM_CASE(0, 1)
+  DVST_GEMM_CASE(1, 0)
+  DVST_GEMM_CASE(1, 1)
+  DVST_GEMM_CASE(2, 0)
+  DVST_GEMM_CASE(2, 1)
+#undef DVST_GEMM_CASE
+  return set_error("gemm: unsupported epilogue");
 }
 
 }  // namespace dvst
