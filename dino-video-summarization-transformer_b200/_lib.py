@@ -28,6 +28,7 @@ SIGNATURES = {
     "dvst_gemm_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
                                c_void_p, c_ll, c_int, c_ll, c_int, c_void_p]),
     "dvst_set_gemm_cta_group": (None, [c_int]),
+    "dvst_set_attention_impl": (None, [c_int]),
     "dvst_set_chunk_rows": (None, [c_ll]),
     "dvst_profile_enable": (None, [c_int]),
     "dvst_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),

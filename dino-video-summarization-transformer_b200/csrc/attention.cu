@@ -19,7 +19,6 @@ namespace dvst {
 namespace {
 
 constexpr int HD = 64;     // head dim
-constexpr int QKV_LD = 2304;
 constexpr int DMODEL = 768;
 
 struct AttnParams {
@@ -521,6 +520,12 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
   static size_t cur_t = 0, cur1 = 0, cur1s = 0, cur4 = 0, cur4s = 0;
   const size_t per = static_cast<size_t>(S_pad) * 128;
   int rc = 0;
+  if (!split && (mode == 1 || mode == 3)) {
+    rc = launch_spatial_attention_sm100(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, st);
+    if (rc == 0) { count_launch(); return 0; }
+    if (rc != 1) return rc;
+    rc = 0;
+  }
   if (mode == 0 && S_pad <= 48 && !split) {
     // contiguous-sequence kernel
     const size_t smem = static_cast<size_t>(S_pad) * TROW;

@@ -1,0 +1,437 @@
+// tcgen05 / TMEM spatial attention for sm_100a: softmax(q k^T / 8) v over the 1 + N tokens of one frame (divided
+// space-time attention's spatial half, models/timesformer.py:140-164, and space_only, :120-123), one (frame, head)
+// problem at a time on a persistent CTA per SM.
+//
+// Token layout: the N patch rows of sequence (b, t) are rows (b*N + n)*T + t of the packed qkv matrix - a stride-T row
+// gather that one 3-D TMA box (64 columns x 1 frame x N patches, SWIZZLE_128B) pulls straight into shared memory; the
+// CLS row is copied behind them (attention is invariant to the key order, so CLS is token N here, not token 0).
+//
+//   S = Q K^T   : tcgen05.mma  M = 128 (x2 row tiles), N = NPAD (= 1 + N rounded up to 16), K = 64   -> TMEM fp32
+//   softmax     : one thread per query row (tcgen05.ld 32x32b), row max, exp2, row sum; P (bf16) is written back
+//                 over S in TMEM (tcgen05.st) - scores and probabilities never touch shared or global memory
+//   O = P V     : tcgen05.mma with A = P from TMEM, B = V from shared memory as an MN-major operand (V rows are keys,
+//                 i.e. the K dimension, so no transpose copy), M = 128, N = 64, K = NPAD               -> TMEM fp32
+//   epilogue    : tcgen05.ld O, scale by 1 / row sum, bf16, swizzled staging tile, 3-D TMA store back to the token rows
+//
+// Warp roles (384 threads): warp 0 TMA producer + CLS-row copy, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+// softmax / epilogue of row tile A (rows 0-127), warps 8-11 of row tile B (rows 128-255).  TMEM: 2 x 256 columns; per
+// tile S occupies [0, NPAD), P overwrites [0, NPAD/2), O lands in [128, 192) once S has been consumed.
+// Shared memory: 2 stages of {Q, K, V} so the loads of problem i+1 overlap the math of problem i.
+#include "dvst_internal.h"
+#include "ptx.cuh"
+
+namespace dvst {
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int DMODEL = 768;
+constexpr int TILE_BYTES = 128 * 128;   // one 128-row tile of 128-byte rows
+constexpr int O_COL = 128;              // TMEM column of the O accumulator inside a tile's 256-column region
+constexpr int NUM_THREADS = 384;
+
+struct SpParams {
+  const __nv_bfloat16* qkv;
+  long long ld;
+  __nv_bfloat16* out;   // space-only: CLS rows are ordinary bf16 output rows
+  long long ldo;
+  float* cls_out;       // divided: [B*T, 768] fp32 CLS attention outputs (averaged over frames by the caller)
+  int mode;             // 1 divided-spatial, 3 space-only
+  int S, N, NPAD, T;
+  int n_prob, heads;
+  long long cls_base;
+  int rows_a, rows_b;   // patch rows of tile A / tile B (what the TMA stores cover)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// V as the B operand of O = P V: B is [N = 64 head dims] x [K = 16 keys]; in shared memory the keys are rows of 128
+// bytes (64 dims) with the TMA 128-byte swizzle, i.e. the canonical MN-major SWIZZLE_128B layout
+// ((8 chunks of 16 B along MN), (8 keys, k)) : ((1, LBO), (128 B, SBO)) with one MN atom (LBO unused) and SBO = 1024 B
+// between 8-key groups.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;            // leading byte offset (single MN atom: unused)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // stride byte offset: next group of 8 keys
+  d |= static_cast<uint64_t>(1) << 46;            // descriptor version 1 (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOutA,
+                               const __grid_constant__ CUtensorMap tmOutB, const SpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const int n_tiles = p.S > 128 ? 2 : 1;
+  const uint32_t q_bytes = n_tiles * TILE_BYTES;
+  const uint32_t kv_bytes = (static_cast<uint32_t>(p.NPAD) * 128u + 1023u) & ~1023u;
+  const uint32_t stage_bytes = q_bytes + 2 * kv_bytes;
+  const uint32_t sO = base + 2 * stage_bytes;          // output staging, one 128-row tile per row tile
+  const uint32_t bars = sO + n_tiles * TILE_BYTES;
+  const uint32_t full_bar = bars;            // [2]  TMA + CLS copy -> MMA
+  const uint32_t empty_bar = bars + 16;      // [2]  MMA (all reads of the stage done) -> producer
+  const uint32_t sfull_bar = bars + 32;      // [2 tiles]  S ready
+  const uint32_t pfull_bar = bars + 48;      // [2 tiles]  P written
+  const uint32_t ofull_bar = bars + 64;      // [2 tiles]  O ready
+  const uint32_t oempty_bar = bars + 80;     // [2 tiles]  O read out: the tile's TMEM region may be overwritten
+  const uint32_t tmem_slot = bars + 96;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.S, N = p.N, NPAD = p.NPAD;
+  // warps of a row tile that own at least one real query row
+  const int act_a = min(4, (min(S, 128) + 31) >> 5);
+  const int act_b = n_tiles == 2 ? (S - 128 + 31) >> 5 : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmOutA);
+    tma_prefetch_desc(&tmOutB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(sfull_bar, 1);
+    mbar_init(sfull_bar + 8, 1);
+    mbar_init(pfull_bar, act_a);
+    mbar_init(pfull_bar + 8, act_b > 0 ? act_b : 1);
+    mbar_init(ofull_bar, 1);
+    mbar_init(ofull_bar + 8, 1);
+    mbar_init(oempty_bar, act_a);
+    mbar_init(oempty_bar + 8, act_b > 0 ? act_b : 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  // K / V rows [S, NPAD) are never written by the loads: zero them once (P is 0 there, and 0 * garbage must not be NaN)
+  for (int s = 0; s < 2; ++s) {
+    const int pad_chunks = (NPAD - S) * 8;
+    for (int i = threadIdx.x; i < 2 * pad_chunks; i += NUM_THREADS) {
+      const int which = i / pad_chunks, j = i - which * pad_chunks;
+      uint8_t* dst = smem + s * stage_bytes + q_bytes + which * kv_bytes + (S * 128 + j * 16);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== producer: 3 TMA boxes (Q, K, V patch rows) + the CLS row of each =====
+    int it = 0;
+    for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int seq = prob / p.heads, head = prob - seq * p.heads;
+      const int b = seq / p.T, t = seq - b * p.T;
+      if (lane == 0) mbar_wait(empty_bar + 8 * s, ph ^ 1);
+      __syncwarp();
+      const uint32_t st = base + s * stage_bytes;
+      if (lane == 0) {
+        tma_load_3d(st, &tmIn, full_bar + 8 * s, head * HD, t, b * N);
+        tma_load_3d(st + q_bytes, &tmIn, full_bar + 8 * s, DMODEL + head * HD, t, b * N);
+        tma_load_3d(st + q_bytes + kv_bytes, &tmIn, full_bar + 8 * s, 2 * DMODEL + head * HD, t, b * N);
+      }
+      if (lane < 24) {
+        const int which = lane >> 3, ch = lane & 7;
+        const long long cls_row = p.cls_base + (p.mode == 1 ? b : seq);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + cls_row * p.ld + which * DMODEL + head * HD) + ch);
+        const uint32_t off = (which == 0 ? 0u : q_bytes + (which - 1) * kv_bytes) + N * 128 + ((ch ^ (N & 7)) << 4);
+        *reinterpret_cast<uint4*>(smem + s * stage_bytes + off) = v;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * s, 3u * N * 128u);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc_s = make_idesc(128, NPAD, 0);
+      constexpr uint32_t idesc_pv = make_idesc(128, HD, 1);
+      const int ksteps = NPAD >> 4;
+      int it = 0;
+      for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1, tp = it & 1;
+        const uint32_t st = base + s * stage_bytes;
+        mbar_wait(full_bar + 8 * s, ph);
+        tc_fence_after();
+        for (int tile = 0; tile < n_tiles; ++tile) {
+          mbar_wait(oempty_bar + 8 * tile, tp ^ 1);  // previous problem's O of this tile has been read out
+          tc_fence_after();
+          const uint32_t d = tmem_base + tile * 256;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16<1>(d, make_kmajor_sw128_desc(st + tile * TILE_BYTES + k * 32),
+                         make_kmajor_sw128_desc(st + q_bytes + k * 32), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(sfull_bar + 8 * tile);
+        }
+        for (int tile = 0; tile < n_tiles; ++tile) {
+          mbar_wait(pfull_bar + 8 * tile, tp);
+          tc_fence_after();
+          const uint32_t region = tmem_base + tile * 256;
+          for (int j = 0; j < ksteps; ++j)
+            umma_ts_bf16(region + O_COL, region + j * 8, make_mnmajor_sw128_desc(st + q_bytes + kv_bytes + j * 2048),
+                         idesc_pv, j != 0 ? 1u : 0u);
+          umma_commit(ofull_bar + 8 * tile);
+        }
+        umma_commit(empty_bar + 8 * s);  // every MMA that reads this stage has completed when this fires
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== softmax + epilogue: one thread per query row =====
+    const int tile = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int n_act = tile == 0 ? act_a : act_b;
+    if (tile < n_tiles && q < n_act) {
+      const int rloc = q * 32 + lane;          // row inside the tile
+      const int row = tile * 128 + rloc;       // token index in the sequence (N = CLS)
+      const uint32_t treg = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tile * 256;
+      const uint32_t so_tile = sO + tile * TILE_BYTES;
+      const bool store_leader = q == 0 && lane == 0;
+      const int rows_tile = tile == 0 ? p.rows_a : p.rows_b;
+      const float scale_log2 = 0.125f * 1.4426950408889634f;
+      const int nch = (NPAD + 31) >> 5;
+      int it = 0;
+      for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++it) {
+        const uint32_t tp = it & 1;
+        const int seq = prob / p.heads, head = prob - seq * p.heads;
+        const int b = seq / p.T, t = seq - b * p.T;
+        mbar_wait(sfull_bar + 8 * tile, tp);
+        tc_fence_after();
+        // ---- pass 1: row max ----
+        float mx = -INFINITY;
+        {
+          uint32_t v[32], v2[32];
+          tmem_ld_32x32(treg, v);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c < nch) {
+              uint32_t (&cur)[32] = (c & 1) ? v2 : v;
+              uint32_t (&nxt)[32] = (c & 1) ? v : v2;
+              tmem_ld_wait();
+              if (c + 1 < nch) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
+              if (c * 32 + 32 <= S) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c * 32 + j < S) mx = fmaxf(mx, __uint_as_float(cur[j]));
+              }
+            }
+          }
+        }
+        // ---- pass 2: p = exp2((s - max) * scale), row sum, P -> TMEM (bf16 pairs over the consumed S columns) ----
+        const float moff = mx * scale_log2;
+        float sum = 0.f;
+        {
+          uint32_t v[32], v2[32];
+          tmem_ld_32x32(treg, v);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c < nch) {
+              uint32_t (&cur)[32] = (c & 1) ? v2 : v;
+              uint32_t (&nxt)[32] = (c & 1) ? v : v2;
+              tmem_ld_wait();
+              if (c + 1 < nch) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
+              float e[32];
+              if (c * 32 + 32 <= S) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(cur[j]), scale_log2, -moff));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  e[j] = c * 32 + j < S ? ex2_approx(fmaf(__uint_as_float(cur[j]), scale_log2, -moff)) : 0.f;
+              }
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                sum += e[2 * j] + e[2 * j + 1];
+                pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+              }
+              tmem_st_32x16(treg + c * 16, pk);
+            }
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pfull_bar + 8 * tile);
+        // ---- O ----
+        mbar_wait(ofull_bar + 8 * tile, tp);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(treg + O_COL, o0);
+        tmem_ld_32x32(treg + O_COL + 32, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(oempty_bar + 8 * tile);
+        const float inv = 1.0f / sum;
+        // the previous problem's TMA store must have finished reading the staging tile
+        if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        named_bar_sync(1 + tile, n_act * 32);
+        if (row < N) {
+          const uint32_t dst = so_tile + rloc * 128;
+          const int sw = rloc & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t (&o)[32] = j < 4 ? o0 : o1;
+            const int j8 = (j & 3) * 8;
+            const uint32_t w0 = pack_bf16x2(__uint_as_float(o[j8]) * inv, __uint_as_float(o[j8 + 1]) * inv);
+            const uint32_t w1 = pack_bf16x2(__uint_as_float(o[j8 + 2]) * inv, __uint_as_float(o[j8 + 3]) * inv);
+            const uint32_t w2 = pack_bf16x2(__uint_as_float(o[j8 + 4]) * inv, __uint_as_float(o[j8 + 5]) * inv);
+            const uint32_t w3 = pack_bf16x2(__uint_as_float(o[j8 + 6]) * inv, __uint_as_float(o[j8 + 7]) * inv);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ sw) << 4)), "r"(w0), "r"(w1),
+                         "r"(w2), "r"(w3) : "memory");
+          }
+        } else if (row == N) {
+          if (p.mode == 1) {
+            float* dst = p.cls_out + static_cast<long long>(seq) * DMODEL + head * HD;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t (&o)[32] = j < 8 ? o0 : o1;
+              const int j4 = (j & 7) * 4;
+              *reinterpret_cast<float4*>(dst + j * 4) =
+                  make_float4(__uint_as_float(o[j4]) * inv, __uint_as_float(o[j4 + 1]) * inv,
+                              __uint_as_float(o[j4 + 2]) * inv, __uint_as_float(o[j4 + 3]) * inv);
+            }
+          } else {
+            __nv_bfloat16* dst = p.out + (p.cls_base + seq) * p.ldo + head * HD;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t (&o)[32] = j < 4 ? o0 : o1;
+              const int j8 = (j & 3) * 8;
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o[j8]) * inv, __uint_as_float(o[j8 + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(o[j8 + 2]) * inv, __uint_as_float(o[j8 + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(o[j8 + 4]) * inv, __uint_as_float(o[j8 + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(o[j8 + 6]) * inv, __uint_as_float(o[j8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + j * 8) = w;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + tile, n_act * 32);
+        if (store_leader && rows_tile > 0) {
+          tma_store_3d(tile == 0 ? &tmOutA : &tmOutB, so_tile, head * HD, t, b * N + tile * 128);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+static int g_attention_impl = 1;  // 1 = tcgen05 kernel where it applies, 0 = mma.sync kernels only
+void set_attention_impl(int impl) { g_attention_impl = impl != 0 ? 1 : 0; }
+
+// Returns 1 if the shape is not handled here (the caller falls back to the mma.sync kernels), 0 on success, < 0 error.
+int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode,
+                                   int B, int T, int N, long long cls_base, cudaStream_t st) {
+  if (!g_attention_impl) return 1;
+  const int S = N + 1;
+  if ((mode != 1 && mode != 3) || S > 256 || N < 1) return 1;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (ld % 8) || (ldo % 8))
+    return 1;
+  SpParams p;
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.ld = ld;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.cls_out = cls_out;
+  p.mode = mode;
+  p.S = S; p.N = N; p.NPAD = (S + 15) & ~15; p.T = T;
+  p.heads = 12;
+  p.n_prob = B * T * p.heads;
+  p.cls_base = cls_base;
+  p.rows_a = N < 128 ? N : 128;
+  p.rows_b = N > 128 ? N - 128 : 0;
+  if (p.n_prob <= 0) return 0;
+  const int n_tiles = S > 128 ? 2 : 1;
+  const size_t kv_bytes = (static_cast<size_t>(p.NPAD) * 128 + 1023) & ~static_cast<size_t>(1023);
+  const size_t smem = 1024 + 2 * (n_tiles * TILE_BYTES + 2 * kv_bytes) + n_tiles * TILE_BYTES + 128;
+  static size_t cur = 0;
+  if (smem > cur) {
+    cudaError_t e = cudaFuncSetAttribute(spatial_attention_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error("attention(sm100) attr: %s", cudaGetErrorString(e));
+    cur = smem;
+  }
+  const uint64_t BN = static_cast<uint64_t>(B) * N;
+  CUtensorMap tmIn, tmOutA, tmOutB;
+  if (int rc = make_tmap_bf16_3d(&tmIn, qkv, 3 * DMODEL, T, BN, ld * 2, static_cast<uint64_t>(T) * ld * 2, HD, 1, N))
+    return rc;
+  if (int rc = make_tmap_bf16_3d(&tmOutA, out, DMODEL, T, BN, ldo * 2, static_cast<uint64_t>(T) * ldo * 2, HD, 1,
+                                 p.rows_a))
+    return rc;
+  if (int rc = make_tmap_bf16_3d(&tmOutB, out, DMODEL, T, BN, ldo * 2, static_cast<uint64_t>(T) * ldo * 2, HD, 1,
+                                 p.rows_b > 0 ? p.rows_b : 1))
+    return rc;
+  const int grid = p.n_prob < num_sms() ? p.n_prob : num_sms();
+  spatial_attention_sm100_kernel<<<grid, NUM_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : set_error("attention(sm100) launch: %s", cudaGetErrorString(e));
+}
+
+}  // namespace dvst

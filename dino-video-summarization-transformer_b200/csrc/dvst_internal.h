@@ -65,6 +65,12 @@ int launch_embed_table(const float* pos, int P, const float* time_embed, int T0,
 int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                      int N, long long cls_base, int split, cudaStream_t st);
 
+// tcgen05 / TMEM kernel for modes 1 and 3 (bf16): returns 0 when it ran, 1 when the shape is not covered (callers then
+// use the mma.sync kernels), anything else is an error code.
+int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode,
+                                   int B, int T, int N, long long cls_base, cudaStream_t st);
+void set_attention_impl(int impl);  // 1 (default) = tcgen05 where it applies, 0 = mma.sync kernels only; test hook
+
 long long head_loss_scratch_bytes(int P);
 int launch_head_loss(const void* zs, const void* zt, long long ldz, const void* w, const float* center, float tt,
                      float ts, int P, int out_dim, float* loss, void* scratch, long long scratch_bytes,
@@ -72,5 +78,7 @@ int launch_head_loss(const void* zs, const void* zt, long long ldz, const void* 
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols);
+int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 
 }  // namespace dvst

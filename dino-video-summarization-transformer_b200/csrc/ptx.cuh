@@ -39,12 +39,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Arrive on the barrier at the same smem offset in another CTA of the cluster.
+// Arrive on the barrier at the same smem offset in another CTA of the cluster.  Default (.release.cta) semantics as in
+// CUTLASS' ClusterBarrier::arrive: the only thing published is "my tcgen05.ld of this TMEM stage have completed"
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it), so no cluster/gpu-scope MEMBAR + ERRBAR is needed
+// (ncu: that fence cost the non-leader CTA's epilogue warps ~12 % of their time).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta_rank) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {

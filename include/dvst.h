@@ -46,6 +46,10 @@ int dvst_abi_version(void);
  * single-CTA 128x256 kernel. */
 void dvst_set_gemm_cta_group(int cg);
 
+/* Tuning / test hook: 1 (default) runs spatial / space-only attention (modes 1 and 3, up to 256 tokens, bf16) on the
+ * tcgen05 + TMEM kernel; 0 forces the mma.sync kernels for every mode. */
+void dvst_set_attention_impl(int impl);
+
 /* L2-residency tuning: walk a batch in chunks of about `rows` token rows (0 = whole batch per pass).  Results are
  * bit-identical for any value (rows of every kernel are independent).  Call before dvst_workspace_bytes. */
 void dvst_set_chunk_rows(long long rows);
