@@ -199,23 +199,30 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
       const uint32_t idesc_s = make_idesc(128, NPAD, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, HD, 1);
       const int ksteps = NPAD >> 4;
+      auto issue_s = [&](int tile, uint32_t st) {
+        const uint32_t d = tmem_base + tile * 256;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16<1>(d, make_kmajor_sw128_desc(st + tile * TILE_BYTES + k * 32),
+                       make_kmajor_sw128_desc(st + q_bytes + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(sfull_bar + 8 * tile);
+      };
+      // Software-pipelined issue order: S of problem i+1 for a row tile goes out as soon as that tile's O of problem i
+      // has been read back, i.e. BEFORE waiting for the other tile's P - the two tiles' chains
+      // (S -> softmax -> P V -> read-out -> next S) run decoupled and keep the MUFU busy from either one.
       int it = 0;
+      if (static_cast<int>(blockIdx.x) < p.n_prob) {
+        mbar_wait(full_bar, 0);
+        tc_fence_after();
+        for (int tile = 0; tile < n_tiles; ++tile) issue_s(tile, base);
+      }
       for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++it) {
         const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1, tp = it & 1;
+        const uint32_t tp = it & 1;
         const uint32_t st = base + s * stage_bytes;
-        mbar_wait(full_bar + 8 * s, ph);
-        tc_fence_after();
-        for (int tile = 0; tile < n_tiles; ++tile) {
-          mbar_wait(oempty_bar + 8 * tile, tp ^ 1);  // previous problem's O of this tile has been read out
-          tc_fence_after();
-          const uint32_t d = tmem_base + tile * 256;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16<1>(d, make_kmajor_sw128_desc(st + tile * TILE_BYTES + k * 32),
-                         make_kmajor_sw128_desc(st + q_bytes + k * 32), idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(sfull_bar + 8 * tile);
-        }
+        const bool has_next = prob + static_cast<int>(gridDim.x) < p.n_prob;
+        const int s_next = (it + 1) & 1;
+        const uint32_t ph_next = ((it + 1) >> 1) & 1;
         for (int tile = 0; tile < n_tiles; ++tile) {
           mbar_wait(pfull_bar + 8 * tile, tp);
           tc_fence_after();
@@ -224,8 +231,17 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
             umma_ts_bf16(region + O_COL, region + j * 8, make_mnmajor_sw128_desc(st + q_bytes + kv_bytes + j * 2048),
                          idesc_pv, j != 0 ? 1u : 0u);
           umma_commit(ofull_bar + 8 * tile);
+          if (tile == n_tiles - 1) umma_commit(empty_bar + 8 * s);  // every MMA reading this stage has been issued
+          if (has_next) {
+            if (tile == 0) {
+              mbar_wait(full_bar + 8 * s_next, ph_next);
+              tc_fence_after();
+            }
+            mbar_wait(oempty_bar + 8 * tile, tp);  // this tile's O (problem i) has been read out of TMEM
+            tc_fence_after();
+            issue_s(tile, base + s_next * stage_bytes);
+          }
         }
-        umma_commit(empty_bar + 8 * s);  // every MMA that reads this stage has completed when this fires
       }
     }
   } else if (warp >= 4) {
@@ -250,7 +266,7 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
         mbar_wait(sfull_bar + 8 * tile, tp);
         tc_fence_after();
         // ---- pass 1: row max ----
-        float mx = -INFINITY;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         {
           uint32_t v[32], v2[32];
           tmem_ld_32x32(treg, v);
@@ -263,18 +279,19 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
               if (c + 1 < nch) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
               if (c * 32 + 32 <= S) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(cur[j]));
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (c * 32 + j < S) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                  if (c * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(cur[j]));
               }
             }
           }
         }
         // ---- pass 2: p = exp2((s - max) * scale), row sum, P -> TMEM (bf16 pairs over the consumed S columns) ----
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const float moff = mx * scale_log2;
-        float sum = 0.f;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
         {
           uint32_t v[32], v2[32];
           tmem_ld_32x32(treg, v);
@@ -297,7 +314,7 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
               uint32_t pk[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                sum += e[2 * j] + e[2 * j + 1];
+                sum4[j & 3] += e[2 * j] + e[2 * j + 1];
                 pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
               }
               tmem_st_32x16(treg + c * 16, pk);
@@ -318,7 +335,7 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(oempty_bar + 8 * tile);
-        const float inv = 1.0f / sum;
+        const float inv = 1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
         // the previous problem's TMA store must have finished reading the staging tile
         if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         named_bar_sync(1 + tile, n_act * 32);
