@@ -483,7 +483,126 @@ __global__ void __launch_bounds__(128, 3) temporal_attention_kernel(const AttnPa
   }
 }
 
+// CLS-query-only attention (one warp per (sequence, head)), fp32 CUDA-core math.  Used for the LAST block when only the
+// CLS feature is returned (timesformer.py:342-345 keeps x[:, 0]): the patch-token queries of that block feed nothing, so
+// only the CLS row attends - over the same keys / values as the full kernels.  Each lane walks keys lane, lane + 32, ...
+// with an online softmax (own max / sum / 64 accumulators), lanes are merged at the end with a transposing shuffle
+// reduction that leaves outputs 2*lane, 2*lane + 1 in each lane.  hi/lo inputs (split precision) are summed on load.
+__global__ void __launch_bounds__(128) cls_attention_kernel(const AttnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long prob = static_cast<long long>(blockIdx.x) * 4 + warp;
+  if (prob >= static_cast<long long>(p.n_seq) * p.heads) return;
+  const int seq = static_cast<int>(prob / p.heads), head = static_cast<int>(prob % p.heads);
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+
+  auto load64 = [&](const __nv_bfloat16* src, float (&dst)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + c);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        dst[c * 8 + 2 * j] = __low2float(h);
+        dst[c * 8 + 2 * j + 1] = __high2float(h);
+      }
+    }
+  };
+  auto load_row = [&](long long row, int which, float (&dst)[64]) {
+    const __nv_bfloat16* src = p.qkv + row * p.ld + which * DMODEL + head * HD;
+    load64(src, dst);
+    if (p.split) {
+      float lo[64];
+      load64(src + 3 * DMODEL, lo);
+#pragma unroll
+      for (int d = 0; d < 64; ++d) dst[d] += lo[d];
+    }
+  };
+
+  float q[64];
+  load_row(row_of(p, seq, 0), 0, q);
+#pragma unroll
+  for (int d = 0; d < 64; ++d) q[d] *= scale_log2;
+  float acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int key = lane; key < p.S; key += 32) {
+    const long long row = row_of(p, seq, key);
+    float kv[64];
+    load_row(row, 1, kv);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; d += 4) {
+      s0 = fmaf(q[d], kv[d], s0); s1 = fmaf(q[d + 1], kv[d + 1], s1);
+      s2 = fmaf(q[d + 2], kv[d + 2], s2); s3 = fmaf(q[d + 3], kv[d + 3], s3);
+    }
+    const float sc = (s0 + s1) + (s2 + s3);
+    const float mn = fmaxf(m, sc);
+    const float corr = exp2f(m - mn), pe = exp2f(sc - mn);  // m = -inf on the first key: corr = 0
+    m = mn;
+    l = l * corr + pe;
+    load_row(row, 2, kv);
+#pragma unroll
+    for (int d = 0; d < 64; ++d) acc[d] = fmaf(pe, kv[d], acc[d] * corr);
+  }
+  // merge the lanes
+  float mw = m;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, off));
+  const float sc = m == -INFINITY ? 0.f : exp2f(m - mw);  // lanes without keys contribute nothing
+  l *= sc;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+#pragma unroll
+  for (int d = 0; d < 64; ++d) acc[d] *= sc;
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? acc[i] : acc[i + n];
+      const float keep = upper ? acc[i + n] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  const float inv = 1.0f / l;
+  const float v0 = acc[0] * inv, v1 = acc[1] * inv;  // outputs 2*lane, 2*lane + 1
+  if (p.mode == 1) {
+    float* dst = p.cls_out + static_cast<long long>(seq) * DMODEL + head * HD;
+    *reinterpret_cast<float2*>(dst + 2 * lane) = make_float2(v0, v1);
+  } else {
+    __nv_bfloat16* dst = p.out + row_of(p, seq, 0) * p.ldo + head * HD;
+    const uint32_t hi = pack2(v0, v1);
+    *reinterpret_cast<uint32_t*>(dst + 2 * lane) = hi;
+    if (p.split) *reinterpret_cast<uint32_t*>(dst + p.lo_off + 2 * lane) = pack_lo2(v0, v1, hi);
+  }
+}
+
 }  // namespace
+
+int launch_cls_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                         int N, long long cls_base, int split, cudaStream_t st) {
+  AttnParams p;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  p.ld = ld;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.cls_out = cls_out;
+  p.mode = mode;
+  p.T = T; p.N = N; p.cls_base = cls_base; p.heads = 12;
+  p.split = split; p.lo_off = DMODEL;
+  if (mode == 1 || mode == 3) { p.S = N + 1; p.n_seq = B * T; }
+  else if (mode == 2) { p.S = N * T + 1; p.n_seq = B; }
+  else return set_error("cls attention: bad mode %d", mode);
+  if (p.n_seq <= 0) return 0;
+  const long long n_prob = static_cast<long long>(p.n_seq) * p.heads;
+  ProfScope prof(PROF_ATTENTION, 4.0 * n_prob * static_cast<double>(p.S) * HD, st);
+  cls_attention_kernel<<<static_cast<unsigned>((n_prob + 3) / 4), 128, 0, st>>>(p);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : set_error("cls attention launch: %s", cudaGetErrorString(e));
+}
 
 int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                      int N, long long cls_base, int split, cudaStream_t st) {

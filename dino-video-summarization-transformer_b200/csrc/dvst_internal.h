@@ -65,6 +65,10 @@ int launch_embed_table(const float* pos, int P, const float* time_embed, int T0,
 int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                      int N, long long cls_base, int split, cudaStream_t st);
 
+// Same modes 1..3, but only the CLS query of every sequence attends (last block when only CLS features are returned):
+// mode 1 writes cls_out [B*T, 768] fp32, modes 2 / 3 write the CLS rows of `out`.
+int launch_cls_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                         int N, long long cls_base, int split, cudaStream_t st);
 // tcgen05 / TMEM kernel for modes 1 and 3 (bf16): returns 0 when it ran, 1 when the shape is not covered (callers then
 // use the mma.sync kernels), anything else is an error code.
 int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode,

@@ -269,9 +269,30 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
       DVST_TRY(gemm(w.a, lda, b.tproj_w, b.tproj_b, Mt, D, D, w.x, w.x, D, 1, 0));
     }
     // spatial (or joint / per-frame) attention (:120-123,140-181)
-    DVST_TRY(ln(w.x, b.norm1_w, b.norm1_b, M));
-    DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
     const int mode = att == DVST_ATTN_DIVIDED ? 1 : (att == DVST_ATTN_JOINT ? 2 : 3);
+    DVST_TRY(ln(w.x, b.norm1_w, b.norm1_b, M));
+    if (i + 1 == m->cfg.depth && !get_all) {
+      // Last block, CLS features only (forward() keeps norm(x)[:, 0], :342-345): nothing downstream reads the patch
+      // tokens of this block's spatial / MLP half, so only the CLS rows are carried on - bit-identical CLS output.
+      // Patch rows still provide keys / values: their K | V thirds of the qkv GEMM (N = 1536) plus the full qkv of the
+      // CLS rows, then the CLS-query attention, and proj / LayerNorm / MLP on the n_cls CLS rows alone.
+      const long long wrow = split ? 2LL * D : D;  // elements per weight row
+      __nv_bfloat16* qkv_bf = static_cast<__nv_bfloat16*>(w.qkv);
+      __nv_bfloat16* a_bf = static_cast<__nv_bfloat16*>(w.a);
+      DVST_TRY(gemm(w.a, lda, static_cast<const __nv_bfloat16*>(b.qkv_w) + D * wrow, b.qkv_b + D, Mt, 2 * D, D, nullptr,
+                    qkv_bf + D, ldq, act_kind, 0));
+      DVST_TRY(gemm(a_bf + Mt * lda, lda, b.qkv_w, b.qkv_b, n_cls, 3 * D, D, nullptr, qkv_bf + Mt * ldq, ldq, act_kind, 0));
+      DVST_TRY(launch_cls_attention(w.qkv, ldq, w.a, lda, w.cls_acc, mode, B, T, static_cast<int>(N), Mt, split, st));
+      if (att == DVST_ATTN_DIVIDED)
+        DVST_TRY(launch_cls_mean(w.cls_acc, a_bf + Mt * lda, lda, split, D, B, T, nullptr, st));
+      float* x_cls = w.x + Mt * D;
+      DVST_TRY(gemm(a_bf + Mt * lda, lda, b.proj_w, b.proj_b, n_cls, D, D, x_cls, x_cls, D, 1, 0));
+      DVST_TRY(launch_layernorm768(x_cls, D, b.norm2_w, b.norm2_b, a_bf + Mt * lda, lda, act_kind, D, n_cls, LN_EPS, st));
+      DVST_TRY(gemm(a_bf + Mt * lda, lda, b.fc1_w, b.fc1_b, n_cls, 4 * D, D, nullptr, w.hid, ldh, act_kind, 1));
+      DVST_TRY(gemm(w.hid, ldh, b.fc2_w, b.fc2_b, n_cls, D, 4 * D, x_cls, x_cls, D, 1, 0));
+      continue;
+    }
+    DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
     DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, w.cls_acc, mode, B, T, static_cast<int>(N), Mt, split, st));
     if (att == DVST_ATTN_DIVIDED)
       DVST_TRY(launch_cls_mean(w.cls_acc, static_cast<__nv_bfloat16*>(w.a) + Mt * lda, lda, split, D, B, T, nullptr, st));

@@ -80,6 +80,20 @@ def test_get_all_token_order_vs_oracle(dev):
     assert _rel(got[:, 0], ref[:, 0]) < FEAT_TOL and _rel(got[:, 5], ref[:, 5]) < FEAT_TOL
 
 
+@pytest.mark.parametrize("att", ["divided_space_time", "joint_space_time", "space_only"])
+@pytest.mark.parametrize("prec", ["bf16", "high"])
+def test_cls_only_last_block_matches_full_forward(dev, att, prec):
+    """forward() carries only the CLS rows through the last block's spatial / MLP half (the patch tokens of that block
+    feed nothing, timesformer.py:342-345); the result must equal the CLS row of the full get_all forward, where every
+    token is computed: fp32 CUDA-core CLS attention vs tensor-core attention differ by bf16 rounding of P only."""
+    m = build(dev, 3, 2, att, prec)
+    x = synth_clips(21, 2, 4).to(dev)
+    with torch.no_grad():
+        cls_only = m(x)
+        full = m.forward_features(x, get_all=True)[:, 0]
+    assert _rel(cls_only, full) < (3e-3 if prec == "bf16" else 2e-5)
+
+
 def test_reference_smoke_shape(dev):
     """models/timesformer.py:639-643: ones [2,3,8,224,224] -> [2,768]."""
     m = build(dev, 1, 2)
