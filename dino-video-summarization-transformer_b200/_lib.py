@@ -39,6 +39,8 @@ SIGNATURES = {
     "dvst_workspace_bytes": (c_ll, [c_void_p, c_int, c_int, c_int, c_int]),
     "dvst_forward_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_ll,
                                       c_void_p]),
+    "dvst_forward_attention_map": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_ll,
+                                           c_void_p]),
     "dvst_pair_loss": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_float, c_float, c_int, c_int, c_void_p,
                                c_void_p]),
     "dvst_forward_windows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

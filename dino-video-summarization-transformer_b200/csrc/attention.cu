@@ -579,7 +579,100 @@ __global__ void __launch_bounds__(128) cls_attention_kernel(const AttnParams p) 
   }
 }
 
+// Attention MAP of one (sequence, head): softmax(q k^T / 8) written out as fp32 [S, S] in the reference's token order
+// (CLS first) - forward_features(get_attn=True) returns the last block's spatial map for visualisation
+// (models/timesformer.py:155-157,325-331).  Not a hot path: fp32 CUDA-core math, K staged in shared memory as fp32.
+__global__ void __launch_bounds__(256) attention_probs_kernel(const AttnParams p, float* __restrict__ probs) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* sK = reinterpret_cast<float*>(smem);            // [S][65]
+  float* sQ = sK + static_cast<size_t>(p.S) * 65;         // [8 warps][64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.x / p.heads, head = blockIdx.x % p.heads;
+  const int S = p.S;
+  auto load2 = [&](long long row, int which, int d) {  // elements d, d + 1 of q (0) / k (1) of token `row`
+    const __nv_bfloat16* src = p.qkv + row * p.ld + which * DMODEL + head * HD + d;
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(src);
+    float2 f = __bfloat1622float2(h);
+    if (p.split) {
+      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + 3 * DMODEL));
+      f.x += g.x; f.y += g.y;
+    }
+    return f;
+  };
+  for (int idx = threadIdx.x; idx < S * 32; idx += 256) {
+    const int key = idx >> 5, d = (idx & 31) * 2;
+    const float2 f = load2(row_of(p, seq, key), 1, d);
+    sK[key * 65 + d] = f.x;
+    sK[key * 65 + d + 1] = f.y;
+  }
+  __syncthreads();
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+  float* out = probs + (static_cast<size_t>(seq) * p.heads + head) * S * S;
+  for (int i = warp; i < S; i += 8) {
+    const float2 qf = load2(row_of(p, seq, i), 0, lane * 2);
+    sQ[warp * 64 + lane * 2] = qf.x * scale_log2;
+    sQ[warp * 64 + lane * 2 + 1] = qf.y * scale_log2;
+    __syncwarp();
+    float sc[8];  // S <= 256
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = c * 32 + lane;
+      float a = -INFINITY;
+      if (j < S) {
+        a = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) a = fmaf(sQ[warp * 64 + d], sK[j * 65 + d], a);
+      }
+      sc[c] = a;
+      mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      sc[c] = c * 32 + lane < S ? exp2f(sc[c] - mx) : 0.f;
+      sum += sc[c];
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c * 32 + lane < S) out[static_cast<size_t>(i) * S + c * 32 + lane] = sc[c] * inv;
+    __syncwarp();
+  }
+}
+
 }  // namespace
+
+int launch_attention_probs(const void* qkv, long long ld, float* probs, int B, int T, int N, long long cls_base,
+                           int split, cudaStream_t st) {
+  AttnParams p;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  p.ld = ld;
+  p.out = nullptr; p.ldo = 0; p.cls_out = nullptr;
+  p.mode = 1;
+  p.T = T; p.N = N; p.cls_base = cls_base; p.heads = 12;
+  p.split = split; p.lo_off = DMODEL;
+  p.S = N + 1; p.n_seq = B * T;
+  if (p.n_seq <= 0) return 0;
+  if (p.S > 256) return set_error("attention map: %d tokens per frame exceed the supported 256", p.S);
+  const size_t smem = (static_cast<size_t>(p.S) * 65 + 8 * 64) * sizeof(float);
+  static size_t cur = 0;
+  if (smem > cur) {
+    cudaError_t ee = cudaFuncSetAttribute(attention_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem));
+    if (ee != cudaSuccess) return set_error("attention map attr: %s", cudaGetErrorString(ee));
+    cur = smem;
+  }
+  ProfScope prof(PROF_ATTENTION, 2.0 * p.n_seq * p.heads * static_cast<double>(p.S) * p.S * HD, st);
+  attention_probs_kernel<<<static_cast<unsigned>(p.n_seq * p.heads), 256, smem, st>>>(p, probs);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : set_error("attention map launch: %s", cudaGetErrorString(e));
+}
 
 int launch_cls_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                          int N, long long cls_base, int split, cudaStream_t st) {

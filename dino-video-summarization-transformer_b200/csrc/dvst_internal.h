@@ -69,6 +69,9 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
 // mode 1 writes cls_out [B*T, 768] fp32, modes 2 / 3 write the CLS rows of `out`.
 int launch_cls_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                          int N, long long cls_base, int split, cudaStream_t st);
+// Spatial attention map softmax(q k^T / 8) of every (frame, head), fp32 [B*T, 12, 1+N, 1+N], CLS token first.
+int launch_attention_probs(const void* qkv, long long ld, float* probs, int B, int T, int N, long long cls_base,
+                           int split, cudaStream_t st);
 // tcgen05 / TMEM kernel for modes 1 and 3 (bf16): returns 0 when it ran, 1 when the shape is not covered (callers then
 // use the mma.sync kernels), anything else is an error code.
 int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode,

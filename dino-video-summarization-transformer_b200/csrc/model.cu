@@ -171,12 +171,21 @@ long long dvst_workspace_bytes(const dvst_model* h, int B, int T, int H, int W) 
   return static_cast<long long>(carve(*m, nullptr, cb, T, H / 16, W / 16).total);
 }
 
+// get_all: 0 = CLS features, 1 = every token, 2 = attention map of the last block's spatial attention (get_attn)
 static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
                         int get_all, void* workspace, long long workspace_bytes, void* stream);
 
 int dvst_forward_features(dvst_model* h, const float* x_in, int B, int T, int H, int W, float* out, int get_all,
                           void* workspace, long long workspace_bytes, void* stream) {
   return forward_impl(h, x_in, nullptr, B, T, H, W, out, get_all, workspace, workspace_bytes, stream);
+}
+
+int dvst_forward_attention_map(dvst_model* h, const float* x_in, int B, int T, int H, int W, float* attn,
+                               void* workspace, long long workspace_bytes, void* stream) {
+  if (h != nullptr && reinterpret_cast<Model*>(h)->cfg.attention_type != DVST_ATTN_DIVIDED)
+    return set_error("dvst_forward_attention_map: only divided_space_time blocks return an attention map "
+                     "(models/timesformer.py:120-123 ignores return_attn for the other types)");
+  return forward_impl(h, x_in, nullptr, B, T, H, W, attn, 2, workspace, workspace_bytes, stream);
 }
 
 int dvst_forward_windows(dvst_model* h, const float* frames, int F, const int* starts, int n_clips, int T, int H,
@@ -196,12 +205,13 @@ static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int
   const Model* m = reinterpret_cast<const Model*>(h);
   const long long N = static_cast<long long>(H / 16) * (W / 16);
   const int cb = chunk_clips(B, N * T);
-  const long long out_rows = get_all ? 1 + (m->cfg.attention_type == DVST_ATTN_SPACE_ONLY ? N : N * T) : 1;
+  const long long out_rows = get_all == 1 ? 1 + (m->cfg.attention_type == DVST_ATTN_SPACE_ONLY ? N : N * T) : 1;
   for (int b0 = 0; b0 < B; b0 += cb) {
     const int nb = B - b0 < cb ? B - b0 : cb;
     const float* xin = starts ? x_in : x_in + static_cast<long long>(b0) * 3 * T * H * W;
-    const int rc = forward_chunk(h, xin, starts ? starts + b0 : nullptr, nb, T, H, W, out + b0 * out_rows * D, get_all,
-                                 workspace, workspace_bytes, stream);
+    float* o = get_all == 2 ? out + static_cast<long long>(b0) * T * 12 * (N + 1) * (N + 1) : out + b0 * out_rows * D;
+    const int rc = forward_chunk(h, xin, starts ? starts + b0 : nullptr, nb, T, H, W, o, get_all, workspace,
+                                 workspace_bytes, stream);
     if (rc != 0) return rc;
   }
   return 0;
@@ -271,9 +281,14 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
     // spatial (or joint / per-frame) attention (:120-123,140-181)
     const int mode = att == DVST_ATTN_DIVIDED ? 1 : (att == DVST_ATTN_JOINT ? 2 : 3);
     DVST_TRY(ln(w.x, b.norm1_w, b.norm1_b, M));
+    if (i + 1 == m->cfg.depth && get_all == 2) {
+      // get_attn: the last block stops after the spatial q / k and returns softmax(q k^T / 8) (:155-157,325-331)
+      DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
+      return launch_attention_probs(w.qkv, ldq, out, B, T, static_cast<int>(N), Mt, split, st);
+    }
     if (i + 1 == m->cfg.depth && !get_all) {
       // Last block, CLS features only (forward() keeps norm(x)[:, 0], :342-345): nothing downstream reads the patch
-      // tokens of this block's spatial / MLP half, so only the CLS rows are carried on - bit-identical CLS output.
+      // XX
       // Patch rows still provide keys / values: their K | V thirds of the qkv GEMM (N = 1536) plus the full qkv of the
       // CLS rows, then the CLS-query attention, and proj / LayerNorm / MLP on the n_cls CLS rows alone.
       const long long wrow = split ? 2LL * D : D;  // elements per weight row

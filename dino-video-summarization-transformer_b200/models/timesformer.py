@@ -246,9 +246,6 @@ class VisionTransformer(nn.Module):
     # ------------------------------------------------------------------------------------------------------------------
     def forward_features(self, x, get_all=False, get_attn=False):
         """[B,3,T,H,W] -> [B,768] (or [B,1+N*T,768] if get_all) - models/timesformer.py:285-345."""
-        if get_attn:
-            raise NotImplementedError("get_attn (attention-map visualisation, models/timesformer.py:325-331) is not "
-                                      "part of the accelerated scoring path")
         if x.dim() != 5 or x.shape[1] != 3:
             raise ValueError(f"expected input [B,3,T,H,W], got {tuple(x.shape)}")
         if not x.is_cuda:
@@ -266,6 +263,16 @@ class VisionTransformer(nn.Module):
                 self._workspace = None
                 self._workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
             N = (H // 16) * (W // 16)
+            if get_attn:
+                # last block's spatial attention map [B*T, 12, 1+N, 1+N] (models/timesformer.py:325-331,155-157)
+                if self.attention_type != 'divided_space_time':
+                    raise ValueError("get_attn is defined for divided_space_time only (the reference's other block "
+                                     "types ignore return_attn, models/timesformer.py:120-123)")
+                attn = torch.empty(B * T, 12, N + 1, N + 1, dtype=torch.float32, device=x.device)
+                _lib.check(L.dvst_forward_attention_map(self._handle, _lib.ptr(xin), B, T, H, W, _lib.ptr(attn),
+                                                        _lib.ptr(self._workspace), self._workspace.numel(),
+                                                        _lib.cur_stream()))
+                return attn
             if get_all:
                 rows = 1 + (N if self.attention_type == 'space_only' else N * T)
                 out = torch.empty(B, rows, self.embed_dim, dtype=torch.float32, device=x.device)

@@ -84,6 +84,11 @@ long long dvst_workspace_bytes(const dvst_model* m, int B, int T, int H, int W);
 int dvst_forward_features(dvst_model* m, const float* x, int B, int T, int H, int W, float* out, int get_all,
                           void* workspace, long long workspace_bytes, void* stream);
 
+/* forward_features(x, get_attn=True) - models/timesformer.py:325-331,155-157: the softmax(q k^T / 8) map of the LAST
+ * block's spatial attention, attn fp32 [B*T, 12, 1+N, 1+N] (CLS token first), divided_space_time models only. */
+int dvst_forward_attention_map(dvst_model* m, const float* x, int B, int T, int H, int W, float* attn,
+                               void* workspace, long long workspace_bytes, void* stream);
+
 /* Device-side view construction + forward: `frames` is a frame-major video fp32 [F,3,H,W]; clip b is the window of T
  * consecutive frames starting at starts[b] (int32 device array, n_clips entries).  Replaces the materialised
  * [2F,3,G,224,224] view tensor of get_views_of_video_same_size (datasets_custom/dino_loss_loader.py:126-171) followed by

@@ -170,6 +170,30 @@ def forward_features(sd, x, attention_type="divided_space_time", get_all=False):
     return out if get_all else out[:, 0]
 
 
+def attention_map(sd, x):
+    """forward_features(x, get_attn=True), divided_space_time - models/timesformer.py:325-331 with Block.forward's
+    return_attn branch (:155-157): blocks 0..depth-2 run in full, the last block applies its temporal half, then returns
+    softmax(q k^T / 8) of the spatial attention over [cls, N patches] of every frame: [B*T, 12, 1+N, 1+N]."""
+    x = x.to(sd["pos_embed"].dtype)
+    tok, cls = embed_tokens(sd, x, "divided_space_time")
+    B, N, T, D = tok.shape
+    depth = depth_of(sd)
+    for i in range(depth - 1):
+        tok, cls = block_divided(sd, f"blocks.{i}.", tok, cls)
+    pre = f"blocks.{depth - 1}."
+    g = lambda k: sd[pre + k]
+    u = layer_norm(tok, g("temporal_norm1.weight"), g("temporal_norm1.bias"))
+    q, k, v = linear(u, g("temporal_attn.qkv.weight"), g("temporal_attn.qkv.bias")).split(D, dim=-1)
+    r = linear(mha(q, k, v), g("temporal_attn.proj.weight"), g("temporal_attn.proj.bias"))
+    tok = tok + linear(r, g("temporal_fc.weight"), g("temporal_fc.bias"))
+    seq = torch.cat([cls[:, None, None, :].expand(B, T, 1, D), tok.permute(0, 2, 1, 3)], dim=2)  # [B,T,1+N,D]
+    u = layer_norm(seq, g("norm1.weight"), g("norm1.bias"))
+    q, k, _ = linear(u, g("attn.qkv.weight"), g("attn.qkv.bias")).split(D, dim=-1)
+    qh = q.reshape(B * T, N + 1, HEADS, HEAD_DIM).transpose(1, 2)
+    kh = k.reshape(B * T, N + 1, HEADS, HEAD_DIM).transpose(1, 2)
+    return torch.softmax((qh @ kh.transpose(-1, -2)) * (HEAD_DIM ** -0.5), dim=-1)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # DINO head and losses
 # ---------------------------------------------------------------------------------------------------------------------

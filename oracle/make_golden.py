@@ -72,6 +72,22 @@ def gen_backbone():
     return cache
 
 
+def gen_attn():
+    """forward_features(x, get_attn=True) of the unmodified reference (last block's spatial attention map)."""
+    sd = synth_backbone_state_dict(1, depth=2, num_frames=8, attention_type="divided_space_time")
+    m = ref_backbone(sd, 2, 8, 224, "divided_space_time")
+    out = {}
+    with torch.no_grad():
+        a96 = m.forward_features(synth_clips(110, 1, 2, 96, 96), get_attn=True)      # [2, 12, 37, 37]
+        a224 = m.forward_features(synth_clips(111, 1, 2, 224, 224), get_attn=True)   # [2, 12, 197, 197]
+    out["crop96"] = dict(seed_w=1, depth=2, num_frames=8, seed_x=110, B=1, T=2, crop=96, attn=a96.clone())
+    rows = [0, 5, 196]
+    out["crop224_rows"] = dict(seed_w=1, depth=2, num_frames=8, seed_x=111, B=1, T=2, crop=224, rows=rows,
+                               attn=a224[:, :, rows, :].clone())
+    torch.save(out, os.path.join(GOLD, "attn_map.pt"))
+    print("attn", tuple(a96.shape), tuple(a224.shape), float(a96.sum(-1).mean()))
+
+
 def gen_head_loss(models):
     """DINOHead logits summary + scoring losses (mode R and mode H) + training loss / center update."""
     out = {}
@@ -207,7 +223,7 @@ def gen_driver(models):
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["backbone", "head", "windows", "selection", "driver"]
+    what = sys.argv[1:] or ["backbone", "head", "windows", "selection", "driver", "attn"]
     models = gen_backbone() if ("backbone" in what or "head" in what) else None
     if "head" in what:
         gen_head_loss(models)
@@ -217,3 +233,5 @@ if __name__ == "__main__":
         gen_selection()
     if "driver" in what:
         gen_driver(models)
+    if "attn" in what:
+        gen_attn()

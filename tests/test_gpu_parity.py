@@ -94,6 +94,26 @@ def test_cls_only_last_block_matches_full_forward(dev, att, prec):
     assert _rel(cls_only, full) < (3e-3 if prec == "bf16" else 2e-5)
 
 
+@pytest.mark.parametrize("prec", ["bf16", "high"])
+def test_attention_map_vs_reference_golden(dev, prec):
+    """forward_features(x, get_attn=True): last block's spatial attention map, against the reference's own output."""
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "attn_map.pt"))
+    for name, c in G.items():
+        m = build(dev, c["seed_w"], c["depth"], "divided_space_time", prec, c["num_frames"])
+        x = synth_clips(c["seed_x"], c["B"], c["T"], c["crop"], c["crop"]).to(dev)
+        with torch.no_grad():
+            a = m.forward_features(x, get_attn=True)
+        N = (c["crop"] // 16) ** 2
+        assert tuple(a.shape) == (c["B"] * c["T"], 12, N + 1, N + 1) and a.dtype == torch.float32
+        assert (a.sum(-1) - 1).abs().max().item() < 1e-5
+        if "rows" in c:
+            a = a[:, :, c["rows"], :]
+        assert _rel(a, c["attn"]) < (FEAT_TOL if prec == "bf16" else 1e-4)
+    with pytest.raises(ValueError):
+        build(dev, 2, 2, "joint_space_time")(x)  # sanity: model builds; get_attn on it must raise
+        build(dev, 2, 2, "joint_space_time").forward_features(x, get_attn=True)
+
+
 def test_reference_smoke_shape(dev):
     """models/timesformer.py:639-643: ones [2,3,8,224,224] -> [2,768]."""
     m = build(dev, 1, 2)

@@ -30,6 +30,21 @@ def test_backbone_matches_reference(backbone_gold, name):
     assert ((f - c["feat"]).norm() / c["feat"].norm()).item() < 2e-5
 
 
+def test_attention_map_matches_reference(golden_dir):
+    """forward_features(get_attn=True): the last block's spatial attention map (models/timesformer.py:325-331)."""
+    G = torch.load(os.path.join(golden_dir, "attn_map.pt"))
+    for name, c in G.items():
+        sd = synth_backbone_state_dict(c["seed_w"], depth=c["depth"], num_frames=c["num_frames"])
+        x = synth_clips(c["seed_x"], c["B"], c["T"], c["crop"], c["crop"])
+        with torch.no_grad():
+            a = O.attention_map(sd, x)
+        if "rows" in c:
+            a = a[:, :, c["rows"], :]
+        assert a.shape == c["attn"].shape
+        assert (a - c["attn"]).abs().max().item() < 1e-5
+        assert (a.sum(-1) - 1).abs().max().item() < 1e-5
+
+
 def test_head_and_losses_match_reference(golden_dir):
     G = torch.load(os.path.join(golden_dir, "head_loss.pt"))
     fs, ft = G["feat_s"], G["feat_t"]

@@ -31,6 +31,21 @@ def test_forward_fp64(att, T, crop):
     assert (got - ref).abs().max().item() < 1e-12
 
 
+def test_attention_map_fp64():
+    R = ref_shim.load()
+    sd = synth_backbone_state_dict(1, depth=2, num_frames=8)
+    m = R["VisionTransformer"](img_size=224, num_classes=0, patch_size=16, embed_dim=768, depth=2, num_heads=12,
+                               mlp_ratio=4, qkv_bias=True, norm_layer=functools.partial(torch.nn.LayerNorm, eps=1e-6),
+                               num_frames=8, attention_type="divided_space_time")
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().double()
+    x = synth_clips(4, 1, 3, 96, 96).double()
+    with torch.no_grad():
+        ref = m.forward_features(x, get_attn=True)
+    got = O.attention_map({k: v.double() for k, v in sd.items()}, x)
+    assert got.shape == ref.shape and (got - ref).abs().max().item() < 1e-13
+
+
 def test_head_and_loss_fp64():
     R = ref_shim.load()
     hsd = synth_head_state_dict(2, out_dim=1024)
