@@ -56,6 +56,8 @@ SIGNATURES = {
     "dvst_l2norm_rows": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p]),
     "dvst_layernorm768": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_float,
                                   c_void_p]),
+    "dvst_select_frames": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dvst_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dvst_attention": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p]),
 }
 

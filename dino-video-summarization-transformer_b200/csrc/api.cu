@@ -151,4 +151,20 @@ int dvst_attention(const void* qkv, long long ld, void* out, long long ldo, floa
   return launch_attention(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, 0, static_cast<cudaStream_t>(stream));
 }
 
+int dvst_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int n_videos,
+                       int pre_sampling_rate, int num_frames, int* indices, void* stream) {
+  if (loss == nullptr || n_loss == nullptr || n_unsampled == nullptr || indices == nullptr)
+    return set_error("dvst_select_frames: null argument");
+  return launch_select_frames(loss, ld, n_loss, n_unsampled, n_videos, pre_sampling_rate, num_frames, indices,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int dvst_preprocess_u8(const unsigned char* video, int n_frames, int H, int W, int sampling_rate, const float* mean3,
+                       const float* std3, int crop, float* frames, void* stream) {
+  if (video == nullptr || mean3 == nullptr || std3 == nullptr || frames == nullptr)
+    return set_error("dvst_preprocess_u8: null argument");
+  return launch_preprocess_u8(video, n_frames, H, W, sampling_rate, mean3, std3, crop, frames,
+                              static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

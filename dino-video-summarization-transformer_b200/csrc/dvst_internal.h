@@ -78,6 +78,11 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
                                    int B, int T, int N, long long cls_base, cudaStream_t st);
 void set_attention_impl(int impl);  // 1 (default) = tcgen05 where it applies, 0 = mma.sync kernels only; test hook
 
+int launch_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int V, int rate,
+                         int N, int* out, cudaStream_t st);
+int launch_preprocess_u8(const uint8_t* video, int n, int H, int W, int rate, const float* mean3, const float* std3,
+                         int crop, float* out, cudaStream_t st);
+
 long long head_loss_scratch_bytes(int P);
 int launch_head_loss(const void* zs, const void* zt, long long ldz, const void* w, const float* center, float tt,
                      float ts, int P, int out_dim, float* loss, void* scratch, long long scratch_bytes,

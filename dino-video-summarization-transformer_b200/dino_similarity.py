@@ -88,6 +88,18 @@ def preprocess_frames(video_uint8, sampling_rate=4, mean=(0.45, 0.45, 0.45), std
     """Loader front half (datasets_custom/dino_loss_loader.py:80-92): raw decoded video uint8 [n,H,W,3] -> every
     `sampling_rate`-th frame, /255, mean/std normalised (data_utils.py:308-325), T H W C -> T C H W, centre crop
     (transform.py:206-249, spatial_idx=1).  Runs on whatever device the video tensor lives on (upload uint8, not fp32)."""
+    if video_uint8.is_cuda and video_uint8.dtype == torch.uint8 and video_uint8.dim() == 4 and video_uint8.shape[3] == 3:
+        # one fused kernel (csrc/selection.cu: preprocess_u8_kernel) instead of four full-tensor passes
+        import ctypes
+        v = video_uint8.contiguous()
+        n, h, w = v.shape[0], v.shape[1], v.shape[2]
+        out = torch.empty(-(-n // sampling_rate), 3, crop_size, crop_size, dtype=torch.float32, device=v.device)
+        m3 = (ctypes.c_float * 3)(*[float(x) for x in mean])
+        s3 = (ctypes.c_float * 3)(*[float(x) for x in std])
+        with torch.cuda.device(v.device):
+            _lib.check(_lib.lib().dvst_preprocess_u8(_lib.ptr(v), n, h, w, sampling_rate, m3, s3, crop_size,
+                                                     _lib.ptr(out), _lib.cur_stream()))
+        return out
     frames = video_uint8[::sampling_rate].to(torch.float32) / 255.0
     frames = frames - torch.tensor(mean, dtype=torch.float32, device=frames.device)
     frames = frames / torch.tensor(std, dtype=torch.float32, device=frames.device)

@@ -41,6 +41,33 @@ def select_frames_adaptive(loss_list, n_unsampled, pre_sampling_rate, num_frames
     return indices
 
 
+def select_frames_adaptive_batch(loss_lists, n_unsampled, pre_sampling_rate, num_frames, device="cuda"):
+    """select_frames_adaptive for a whole batch of videos in one kernel launch (dvst_select_frames, csrc/selection.cu):
+    one device thread per video in the reference's fp64 arithmetic, so every index list equals the host function's.
+
+    loss_lists: one loss sequence per video (as stored by export_loss); n_unsampled: frames of each undecimated video.
+    Returns an int32 CUDA tensor [V, num_frames] of frame indices in unsampled-video units."""
+    import torch
+
+    from . import _lib
+    V = len(loss_lists)
+    n_samp = [-(-int(nu) // pre_sampling_rate) for nu in n_unsampled]
+    lens = [min(len(l), ns) for l, ns in zip(loss_lists, n_samp)]
+    fmax = max(lens) if lens else 1
+    host = torch.zeros(V, fmax, dtype=torch.float64)
+    for v, l in enumerate(loss_lists):
+        host[v, :lens[v]] = torch.as_tensor(np.asarray(l, dtype=np.float64)[:lens[v]])
+    dev = torch.device(device)
+    loss = host.to(dev)
+    n_loss = torch.tensor(lens, dtype=torch.int32, device=dev)
+    n_un = torch.tensor([int(x) for x in n_unsampled], dtype=torch.int32, device=dev)
+    out = torch.empty(V, num_frames, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dvst_select_frames(_lib.ptr(loss), fmax, _lib.ptr(n_loss), _lib.ptr(n_un), V,
+                                                 pre_sampling_rate, num_frames, _lib.ptr(out), _lib.cur_stream()))
+    return out
+
+
 def select_frames_uniform(n_sampled, num_frames):
     """Uniform baseline (frame_selection_loader.py:175-185): indices in SAMPLED-frame units, like the reference."""
     interval = int(n_sampled / num_frames)

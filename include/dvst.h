@@ -150,6 +150,22 @@ int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const f
 int dvst_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                    int N, long long cls_base, void* stream);
 
+/* Adaptive frame selection for a batch of videos (datasets_custom/frame_selection_loader.py:115-172) on the device, in
+ * the reference's fp64 arithmetic (numpy pairwise sum, sequential cumsum, first-minimum argmin): identical index lists.
+ *   loss        fp64 [n_videos, ld] device: per-sampled-frame losses of video v in row v (the JSON values; fp32 scores
+ *               widen exactly)
+ *   n_loss      int32 [n_videos] device: losses used per video = min(len(loss list), sampled frames)   (:125-126)
+ *   n_unsampled int32 [n_videos] device: frames of the undecimated video (frames_unsampled.size(0))
+ *   indices     int32 [n_videos, num_frames] device: selected frame indices in unsampled-video units; num_frames <= 64 */
+int dvst_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int n_videos,
+                       int pre_sampling_rate, int num_frames, int* indices, void* stream);
+
+/* Loader front half (datasets_custom/dino_loss_loader.py:80-92) in one pass: decoded video uint8 [n_frames, H, W, 3]
+ * (device) -> every sampling_rate-th frame, / 255, - mean, / std (data_utils.py:308-325), T H W C -> T C H W, centre crop
+ * (transform.py:228-229): frames fp32 [ceil(n_frames / sampling_rate), 3, crop, crop].  mean3 / std3 are HOST pointers. */
+int dvst_preprocess_u8(const unsigned char* video, int n_frames, int H, int W, int sampling_rate, const float* mean3,
+                       const float* std3, int crop, float* frames, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

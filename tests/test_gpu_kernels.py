@@ -187,3 +187,43 @@ def test_colsum_and_center_ema(dev):
     ref = center * 0.9 + bs / 12.0 * 0.1
     _lib.check(L.dvst_center_ema(_lib.ptr(center), _lib.ptr(bs), 12.0, 0.9, 4096, _lib.cur_stream()))
     assert torch.allclose(center, ref, atol=1e-6)
+
+
+def test_batched_selection_matches_reference_goldens(dev, golden_dir):
+    """dvst_select_frames (one device thread per video, numpy-compatible fp64) vs the index lists the reference's
+    FrameSelectionLoader produced (tests/golden/selection.json, 144 videos x N in {8, 16}) and vs the host function on
+    long / adversarial curves (ties, flat curves, collisions running off the end of the video)."""
+    import json
+    import os
+
+    import numpy as np
+    from dvst_b200.frame_selection import select_frames_adaptive, select_frames_adaptive_batch
+    S = json.load(open(os.path.join(golden_dir, "selection.json")))
+    names = sorted(S)
+    for N in (8, 16):
+        got = select_frames_adaptive_batch([S[n]["loss"] for n in names], [S[n]["n_unsampled"] for n in names], 4, N,
+                                           device=dev).cpu().tolist()
+        assert got == [S[n][f"idx{N}"] for n in names]
+    rng = np.random.default_rng(5)
+    curves, nus = [], []
+    for F in (3, 7, 8, 9, 127, 128, 129, 450, 1111):
+        curves.append((rng.random(F).astype(np.float32) + 0.05).astype(np.float64).tolist()); nus.append(4 * F - 1)
+        curves.append([1.0] * F); nus.append(4 * F)                       # flat: exact ties in |cdf - q|
+        spike = [1e-6] * F; spike[F // 2] = 5.0                           # all quantiles collide on one frame
+        curves.append(spike); nus.append(4 * F - 3)
+    for N in (4, 8, 16, 64):
+        got = select_frames_adaptive_batch(curves, nus, 4, N, device=dev).cpu().tolist()
+        assert got == [select_frames_adaptive(c, nu, 4, N) for c, nu in zip(curves, nus)]
+
+
+def test_fused_uint8_preprocess_is_bit_exact(dev):
+    """dvst_preprocess_u8 vs the torch CPU statement of the loader front half (dino_loss_loader.py:80-92): identical
+    fp32 operations, so every value must match bit for bit (odd crop offsets and a non-multiple frame count included)."""
+    from dvst_b200.dino_similarity import preprocess_frames
+    g = torch.Generator().manual_seed(0)
+    for (n, H, W, rate, crop) in [(10, 240, 320, 4, 224), (7, 225, 227, 2, 224), (5, 112, 96, 1, 96)]:
+        raw = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, generator=g)
+        ref = preprocess_frames(raw, rate, crop_size=crop)
+        got = preprocess_frames(raw.to(dev), rate, crop_size=crop)
+        assert got.is_cuda and tuple(got.shape) == tuple(ref.shape)
+        assert torch.equal(got.cpu(), ref)
