@@ -165,6 +165,7 @@ def main_ours(args):
         ge.build()
     if world > 1:
         torch.cuda.set_device(local_rank)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     import dvst_b200  # noqa: F401
