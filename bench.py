@@ -171,7 +171,7 @@ def main_ours(args):
     import dvst_b200  # noqa: F401
     from functools import partial
     from dvst_b200 import _lib
-    from dvst_b200.dino_similarity import DINOLoss, HeadScorer, score_video_device
+    from dvst_b200.dino_similarity import DINOLoss, HeadScorer, score_video_device, score_videos_device
     from dvst_b200.models.timesformer import VisionTransformer
     from dvst_b200.testing import synth_backbone_state_dict, synth_head_state_dict, synth_video
     from dvst_b200.vision_transformer import DINOHead
@@ -308,6 +308,18 @@ def main_ours(args):
                 a1.record()
                 torch.cuda.synchronize()
             aux[f"cfg3_4_3_30_F{F}_videos_per_s_per_gpu"] = 3e3 / a0.elapsed_time(a1)
+        # the same with 8 videos per backbone pass (score_videos_device; identical losses)
+        vids = [synth_video(5 + i, 30).to(dev) for i in range(8)]
+        with torch.no_grad():
+            score_videos_device(model, vids, dl, scorer=scorer)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(3):
+                score_videos_device(model, vids, dl, scorer=scorer)
+            a1.record()
+            torch.cuda.synchronize()
+        aux["cfg3_4_3_30_F30_8_videos_per_pass_videos_per_s_per_gpu"] = 24e3 / a0.elapsed_time(a1)
     if world > 1:
         dist.barrier()
 

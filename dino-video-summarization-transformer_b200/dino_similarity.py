@@ -8,6 +8,8 @@
                         max(F-G+1,1) teacher windows are distinct) and all F losses come back in a single D2H copy
                         instead of one `.item()` sync per frame.  Results are unchanged: every frame's loss is the loss
                         of exactly the (local, global) window pair the reference builds for it.
+  * `score_videos_device` - the same for a batch of videos in one backbone pass per window length (bit-identical
+                        losses; small videos no longer run the GPU at batch 1).
   * `dino_similarity` - the driver loop over a dataset of videos.
 
 Mode R (reference-exact): loss over the 768-d backbone features, tau_t = 0.02, tau_s = 0.3, zero center.
@@ -176,43 +178,103 @@ def _forward_windows(model, frames, starts, T, max_clips):
     return out
 
 
+def _dummy_losses(model, dev, dino_loss, scorer, local_clip_size, global_clip_size):
+    """Malformed video -> the reference's dummy views: `global_clip_size` identical losses of the all-zero
+    (T=local, T=60) pair (dino_loss_loader.py:36-38,103-107; dino_similarity.py:78)."""
+    zs = torch.zeros(local_clip_size, 3, 224, 224, device=dev)
+    zt = torch.zeros(60, 3, 224, 224, device=dev)
+    fs = _forward_windows(model, zs, [0], local_clip_size, 1)
+    ft = _forward_windows(model, zt, [0], 60, 1)
+    idx = torch.zeros(global_clip_size, dtype=torch.int32, device=dev)
+    if scorer is not None:
+        return scorer.pair_losses(fs, ft, idx, idx)
+    return dino_loss.pair_losses(fs, ft, idx, idx)
+
+
+def score_videos_device(model, videos, dino_loss, local_clip_size=3, global_clip_size=30, scorer=None,
+                        max_rows=1 << 19):
+    """Scores a BATCH of videos on the GPU; returns one CUDA tensor [F_v] of per-frame losses per video (no host sync).
+
+    model: dvst_b200 VisionTransformer; videos: list of fp32 [F_v,3,H,W] CUDA tensors (normalised, cropped - what the
+    reference's loader produces before view construction, dino_loss_loader.py:80-92); dino_loss: DINOLoss (mode R) -
+    ignored when a HeadScorer is given (mode H).
+
+    Every video is independent in the reference (dino_similarity.py:66-93 walks them one by one).  Here the student
+    windows of all videos (all T = local) go through the backbone as one batch, the teacher windows as one batch per
+    distinct G = min(global, F_v), and all frames' pair losses come from one launch.  A clip's features do not depend
+    on what else is in its batch (rows of every GEMM / attention tile are independent), so the losses are bit-identical
+    to scoring the videos one at a time."""
+    videos = list(videos)
+    if not videos:
+        return []
+    dev = videos[0].device
+    for v in videos:
+        if not v.is_cuda:
+            raise _lib.DvstError("dvst_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
+        if v.device != dev:
+            raise ValueError("all videos of a batch must live on the same device")
+    out = [None] * len(videos)
+    with torch.cuda.device(dev):
+        good = [i for i, v in enumerate(videos)
+                if v.dim() == 4 and v.shape[0] >= local_clip_size and v.shape[2] == 224 and v.shape[3] == 224]
+        if len(good) < len(videos):
+            dummy = _dummy_losses(model, dev, dino_loss, scorer, local_clip_size, global_clip_size)
+            for i in range(len(videos)):
+                if i not in good:
+                    out[i] = dummy
+        if not good:
+            return out
+        clips = [videos[i].detach().to(torch.float32).contiguous() for i in good]
+        frames = clips[0] if len(clips) == 1 else torch.cat(clips, 0)
+        H, W = frames.shape[2], frames.shape[3]
+        N = (H // 16) * (W // 16)
+        # window starts in units of the concatenated frame axis; windows never cross a video boundary because every
+        # start is clamped to [0, F_v - T] inside its own video (window_starts)
+        s_starts, s_idx = [], []
+        t_starts, t_idx = {}, []       # G -> distinct starts; per frame (G, position inside that G's list)
+        lengths, off = [], 0
+        for c in clips:
+            F = c.shape[0]
+            G, ls, gs = window_starts(F, local_clip_size, global_clip_size)
+            s_pos = {}
+            for j in sorted(set(ls)):
+                s_pos[j] = len(s_starts)
+                s_starts.append(off + j)
+            s_idx += [s_pos[j] for j in ls]
+            lst = t_starts.setdefault(G, [])
+            t_pos = {}
+            for l in sorted(set(gs)):
+                t_pos[l] = len(lst)
+                lst.append(off + l)
+            t_idx += [(G, t_pos[l]) for l in gs]
+            lengths.append(F)
+            off += F
+        fs = _forward_windows(model, frames, s_starts, local_clip_size, max(1, max_rows // (N * local_clip_size)))
+        base, parts = {}, []
+        row = 0
+        for G in sorted(t_starts):
+            base[G] = row
+            parts.append(_forward_windows(model, frames, t_starts[G], G, max(1, max_rows // (N * G))))
+            row += len(t_starts[G])
+        ft = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+        s_idx_t = torch.tensor(s_idx, dtype=torch.int32, device=dev)
+        t_idx_t = torch.tensor([base[G] + p for G, p in t_idx], dtype=torch.int32, device=dev)
+        if scorer is not None:
+            loss = scorer.pair_losses(fs, ft, s_idx_t, t_idx_t)
+        else:
+            loss = dino_loss.pair_losses(fs, ft, s_idx_t, t_idx_t)
+        for i, piece in zip(good, torch.split(loss, lengths)):
+            out[i] = piece
+    return out
+
+
 def score_video_device(model, frames, dino_loss, local_clip_size=3, global_clip_size=30, scorer=None,
                        max_rows=1 << 19):
-    """Scores one video on the GPU; returns the per-frame losses as a CUDA tensor [F] (no host sync).
-
-    model: dvst_b200 VisionTransformer; frames: fp32 [F,3,H,W] CUDA (normalised, cropped - what the reference's loader
-    produces before view construction, dino_loss_loader.py:80-92); dino_loss: DINOLoss (mode R) - ignored when a
-    HeadScorer is given (mode H)."""
+    """Scores one video on the GPU; returns the per-frame losses as a CUDA tensor [F] (no host sync).  See
+    score_videos_device (this is the batch of one)."""
     if not frames.is_cuda:
         raise _lib.DvstError("dvst_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
-    frames = frames.detach().to(torch.float32).contiguous()
-    F, _, H, W = frames.shape
-    dev = frames.device
-    with torch.cuda.device(dev):
-        if F < local_clip_size or H != 224 or W != 224:
-            # malformed video -> the reference's dummy views: `global_clip_size` identical losses of the all-zero
-            # (T=local, T=60) pair (dino_loss_loader.py:36-38,103-107; dino_similarity.py:78)
-            zs = torch.zeros(local_clip_size, 3, 224, 224, device=dev)
-            zt = torch.zeros(60, 3, 224, 224, device=dev)
-            fs = _forward_windows(model, zs, [0], local_clip_size, 1)
-            ft = _forward_windows(model, zt, [0], 60, 1)
-            idx = torch.zeros(global_clip_size, dtype=torch.int32, device=dev)
-            if scorer is not None:
-                return scorer.pair_losses(fs, ft, idx, idx)
-            return dino_loss.pair_losses(fs, ft, idx, idx)
-        G, ls, gs = window_starts(F, local_clip_size, global_clip_size)
-        s_starts = sorted(set(ls))
-        t_starts = sorted(set(gs))
-        N = (H // 16) * (W // 16)
-        fs = _forward_windows(model, frames, s_starts, local_clip_size, max(1, max_rows // (N * local_clip_size)))
-        ft = _forward_windows(model, frames, t_starts, G, max(1, max_rows // (N * G)))
-        s_pos = {v: i for i, v in enumerate(s_starts)}
-        t_pos = {v: i for i, v in enumerate(t_starts)}
-        s_idx = torch.tensor([s_pos[j] for j in ls], dtype=torch.int32, device=dev)
-        t_idx = torch.tensor([t_pos[l] for l in gs], dtype=torch.int32, device=dev)
-        if scorer is not None:
-            return scorer.pair_losses(fs, ft, s_idx, t_idx)
-        return dino_loss.pair_losses(fs, ft, s_idx, t_idx)
+    return score_videos_device(model, [frames], dino_loss, local_clip_size, global_clip_size, scorer, max_rows)[0]
 
 
 def score_video(model, frames, dino_loss=None, local_clip_size=3, global_clip_size=30, scorer=None, **kw):
@@ -223,13 +285,15 @@ def score_video(model, frames, dino_loss=None, local_clip_size=3, global_clip_si
 
 
 def dino_similarity(cfg, local_clip_size, global_clip_size, sampling_rate, file_path, dataset=None, model=None,
-                    scorer=None):
+                    scorer=None, videos_per_batch=8):
     """Driver with the reference's signature (dino_similarity.py:16-93).
 
     Video decoding is outside the accelerated path: `dataset` is any iterable of
     (frames [F,3,224,224] fp32 already sub-sampled by `sampling_rate`, normalised and centre-cropped, file_name).  When
     `model` is None it is built exactly like the reference does (get_vit_base_patch16_224 + "backbone."-stripped
-    checkpoint from cfg.pretrained_weights)."""
+    checkpoint from cfg.pretrained_weights).  `videos_per_batch` videos are scored per backbone pass
+    (score_videos_device: same losses as one at a time) and their F-float loss vectors come back in one D2H copy each;
+    the JSON is still merged video by video in dataset order (export_loss)."""
     from .models import get_vit_base_patch16_224
     if dataset is None:
         raise ValueError("pass `dataset`: an iterable of (frames, file_name); video decoding is not part of this path")
@@ -243,10 +307,22 @@ def dino_similarity(cfg, local_clip_size, global_clip_size, sampling_rate, file_
     dev = next(model.parameters()).device
     dino_loss = DINOLoss(out_dim=768, teacher_temp=0.02, student_temp=0.3).to(dev)
     results = {}
-    for i, (frames, file_name) in enumerate(dataset):
+
+    def flush(batch):
         with torch.no_grad():
-            loss = score_video(model, frames.to(dev, non_blocking=True), dino_loss, local_clip_size, global_clip_size,
-                               scorer=scorer)
-        export_loss(loss, file_name, file_path)
-        results[os.path.splitext(os.path.basename(file_name))[0]] = loss
+            losses = score_videos_device(model, [f for f, _ in batch], dino_loss, local_clip_size, global_clip_size,
+                                         scorer=scorer)
+        for (_, file_name), loss in zip(batch, losses):
+            loss = loss.tolist()
+            export_loss(loss, file_name, file_path)
+            results[os.path.splitext(os.path.basename(file_name))[0]] = loss
+
+    batch = []
+    for frames, file_name in dataset:
+        batch.append((frames.to(dev, non_blocking=True), file_name))
+        if len(batch) >= max(1, int(videos_per_batch)):
+            flush(batch)
+            batch = []
+    if batch:
+        flush(batch)
     return results

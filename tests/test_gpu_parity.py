@@ -10,7 +10,8 @@ import torch
 import dvst_b200  # noqa: F401
 import dvst_oracle as O
 from dvst_b200 import _lib
-from dvst_b200.dino_similarity import (DINOLoss, HeadScorer, preprocess_frames, score_video, score_video_device)
+from dvst_b200.dino_similarity import (DINOLoss, HeadScorer, preprocess_frames, score_video, score_video_device,
+                                       score_videos_device)
 from dvst_b200.frame_selection import select_frames_adaptive
 from dvst_b200.models.timesformer import VisionTransformer
 from dvst_b200.testing import synth_backbone_state_dict, synth_clips, synth_head_state_dict, synth_video
@@ -210,6 +211,26 @@ def test_scoring_vs_oracle_and_selected_indices(dev):
             total += 1
             same += select_frames_adaptive(got, 4 * F, 4, N) == select_frames_adaptive(ref, 4 * F, 4, N)
     assert same == total
+
+
+def test_batched_videos_equal_one_at_a_time(dev):
+    """score_videos_device (several videos per backbone pass, mixed lengths -> mixed teacher window sizes, one
+    malformed video) returns bit-identical losses to scoring each video alone, in both loss modes."""
+    m = build(dev, 1, 2)
+    head = DINOHead(768, 4096)
+    head.load_state_dict(synth_head_state_dict(2, out_dim=4096), strict=True)
+    head = head.to(dev).eval()
+    vids = [synth_video(s, F, smooth=0.5).to(dev) for s, F in ((1, 5), (2, 9), (3, 12), (4, 3))]
+    vids.insert(2, torch.zeros(2, 3, 224, 224, device=dev))  # too short -> dummy
+    dl = DINOLoss(768, 0.02, 0.3).to(dev)
+    for scorer in (None, HeadScorer(head, 0.04, 0.1)):
+        with torch.no_grad():
+            batch = score_videos_device(m, vids, dl, 3, 6, scorer=scorer)
+            single = [score_video_device(m, v, dl, 3, 6, scorer=scorer) for v in vids]
+        assert [len(b) for b in batch] == [5, 9, 6, 12, 3]
+        for b, s in zip(batch, single):
+            assert torch.equal(b, s)
+    assert score_videos_device(m, [], dl) == []
 
 
 def test_train_loss_and_center_update(dev):
