@@ -167,4 +167,25 @@ int dvst_preprocess_u8(const unsigned char* video, int n_frames, int H, int W, i
                               static_cast<cudaStream_t>(stream));
 }
 
+int dvst_knn_similarity(const float* test, long long ldt, const float* train, long long ldr, int n_test, int n_train,
+                        int dim, float* sim, long long lds, void* stream) {
+  if (test == nullptr || train == nullptr || sim == nullptr) return set_error("dvst_knn_similarity: null argument");
+  return launch_knn_similarity(test, ldt, train, ldr, n_test, n_train, dim, sim, lds, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_knn_topk(const float* sim, long long lds, int n_test, int n_train, int k, float* dist, int* idx, int ldk,
+                  void* stream) {
+  if (sim == nullptr || dist == nullptr || idx == nullptr) return set_error("dvst_knn_topk: null argument");
+  return launch_knn_topk(sim, lds, n_test, n_train, k, dist, idx, ldk, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_knn_vote(const float* dist, const int* idx, int ldk, const long long* train_labels,
+                  const long long* test_labels, int n_test, int k, float temperature, int num_classes, int* rank,
+                  int* pred, void* stream) {
+  if (dist == nullptr || idx == nullptr || train_labels == nullptr || test_labels == nullptr || rank == nullptr)
+    return set_error("dvst_knn_vote: null argument");
+  return launch_knn_vote(dist, idx, ldk, train_labels, test_labels, n_test, k, temperature, num_classes, rank, pred,
+                         static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -83,6 +83,15 @@ int launch_select_frames(const double* loss, long long ld, const int* n_loss, co
 int launch_preprocess_u8(const uint8_t* video, int n, int H, int W, int rate, const float* mean3, const float* std3,
                          int crop, float* out, cudaStream_t st);
 
+// weighted k-NN evaluation (knn.cu)
+int launch_knn_similarity(const float* test, long long ldt, const float* train, long long ldr, int n_test, int n_train,
+                          int dim, float* sim, long long lds, cudaStream_t st);
+int launch_knn_topk(const float* sim, long long lds, int n_test, int n_train, int k, float* dist, int* idx, int ldk,
+                    cudaStream_t st);
+int launch_knn_vote(const float* dist, const int* idx, int ldk, const long long* train_labels,
+                    const long long* test_labels, int n_test, int k, float T, int num_classes, int* rank, int* pred,
+                    cudaStream_t st);
+
 long long head_loss_scratch_bytes(int P);
 int launch_head_loss(const void* zs, const void* zt, long long ldz, const void* w, const float* center, float tt,
                      float ts, int P, int out_dim, float* loss, void* scratch, long long scratch_bytes,

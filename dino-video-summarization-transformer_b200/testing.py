@@ -80,3 +80,16 @@ def synth_video(seed, F, H=224, W=224, smooth=0.7):
     for i in range(1, F):
         frames[i] = smooth * frames[i - 1] + (1.0 - smooth ** 2) ** 0.5 * frames[i]
     return frames
+
+
+def synth_knn_features(seed, n_train, n_test, dim=768, num_classes=10, noise=1.0):
+    """L2-normalised class-clustered features + int64 labels shaped like eval_knn's inputs (eval_knn.py:69-74):
+    (train_features [n_train, dim], train_labels, test_features [n_test, dim], test_labels)."""
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.randn(num_classes, dim, generator=g)
+    out = []
+    for n in (n_train, n_test):
+        labels = torch.randint(0, num_classes, (n,), generator=g, dtype=torch.int64)
+        f = centres[labels] + noise * torch.randn(n, dim, generator=g)
+        out += [torch.nn.functional.normalize(f, dim=1, p=2), labels]
+    return tuple(out)

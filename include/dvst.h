@@ -166,6 +166,23 @@ int dvst_select_frames(const double* loss, long long ld, const int* n_loss, cons
 int dvst_preprocess_u8(const unsigned char* video, int n_frames, int H, int W, int sampling_rate, const float* mean3,
                        const float* std3, int crop, float* frames, void* stream);
 
+/* ---- weighted k-NN evaluation of frozen features: knn_classifier, eval_knn.py:138-178 -------------------------------
+ * sim[i,j] = <test[i,:], train[j,:]> in fp32 FMA arithmetic (torch.mm(features, train_features.t()), :153); neighbour
+ * order is the result, so no reduced-precision tensor-core product here.  dim and row strides multiples of 4. */
+int dvst_knn_similarity(const float* test, long long ldt, const float* train, long long ldr, int n_test, int n_train,
+                        int dim, float* sim, long long lds, void* stream);
+/* similarity.topk(k, largest=True, sorted=True) per row (:154): dist fp32 / idx int32 [n_test, ldk], values descending,
+ * equal values by ascending index; k <= 512.  The first k' columns are the top-k' for any k' <= k. */
+int dvst_knn_topk(const float* sim, long long lds, int n_test, int n_train, int k, float* dist, int* idx, int ldk,
+                  void* stream);
+/* Votes of the k nearest neighbours weighted by exp(dist / temperature), summed per class in neighbour order (:155-166),
+ * then rank[i] = position of test_labels[i] in probs.sort(descending) (:167; ties by ascending class index), so that
+ * top1 = #(rank == 0), top5 = #(rank < 5) (:170-172).  pred int32 [n_test] (optional) = predictions[:, 0].
+ * Labels are int64 device arrays (torch.long). */
+int dvst_knn_vote(const float* dist, const int* idx, int ldk, const long long* train_labels,
+                  const long long* test_labels, int n_test, int k, float temperature, int num_classes, int* rank,
+                  int* pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -322,3 +322,29 @@ def select_frames(loss_list, n_unsampled, rate, N, n_sampled=None):
                 break
             s += rate
     return picked
+
+
+def knn_classifier(train_features, train_labels, test_features, test_labels, k, T, num_classes=1000):
+    """Weighted k-NN vote - eval_knn.py:138-178.  similarity = test @ train.T (:153), top-k neighbours (:154; equal
+    similarities by ascending index), per-class sums of exp(sim / T) over the neighbours in order (:155-166), then the
+    position of the true class in the descending sort of the class scores (:167-172; equal scores by ascending class
+    index, i.e. a stable sort).  Returns (top1 %, top5 %, rank [n_test] int64, neighbour indices [n_test, k] int64);
+    the reference returns the first two."""
+    train = train_features.to(torch.float32)
+    test = test_features.to(torch.float32)
+    sim = test @ train.t()
+    order = torch.sort(sim, dim=1, descending=True, stable=True)
+    dist, idx = order.values[:, :k], order.indices[:, :k]
+    w = (dist / T).exp()
+    labels = train_labels.view(-1)[idx]
+    n = test.shape[0]
+    probs = torch.zeros(n, num_classes, dtype=torch.float32)
+    for j in range(k):  # sequential over neighbours like torch.sum over dim 1 of the [B, k, C] product
+        probs[torch.arange(n), labels[:, j]] += w[:, j]
+    tgt = test_labels.view(-1)
+    pt = probs[torch.arange(n), tgt].unsqueeze(1)
+    cls = torch.arange(num_classes).unsqueeze(0)
+    rank = ((probs > pt) | ((probs == pt) & (cls < tgt.unsqueeze(1)))).sum(1)
+    top1 = float((rank == 0).sum()) * 100.0 / n
+    top5 = float((rank < 5).sum()) * 100.0 / n
+    return top1, top5, rank, idx

@@ -222,8 +222,38 @@ def gen_driver(models):
     print("driver", result)
 
 
+KNN_CASES = [  # (seed, n_train, n_test, dim, num_classes, noise, k, T)
+    (1, 600, 200, 64, 10, 4.0, 10, 0.07),
+    (1, 600, 200, 64, 10, 4.0, 20, 0.07),
+    (2, 1500, 300, 768, 101, 6.0, 20, 0.07),
+    (2, 1500, 300, 768, 101, 6.0, 200, 0.07),
+    (3, 400, 100, 32, 6, 2.0, 100, 0.5),
+    (5, 300, 150, 16, 12, 1.5, 3, 0.07),     # fewer voted classes than 5: the zero-score tie order decides top5
+    (4, 257, 130, 20, 7, 1.5, 5, 0.07),
+]
+
+
+def gen_knn():
+    """The reference's knn_classifier (eval_knn.py:138-178, .cuda() mocked to identity) on seeded synthetic features."""
+    from dvst_b200.testing import synth_knn_features
+    knn = ref_shim.load_knn_classifier()
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    out = []
+    try:
+        for (seed, ntr, nte, dim, nc, noise, k, T) in KNN_CASES:
+            trf, trl, tef, tel = synth_knn_features(seed, ntr, nte, dim, nc, noise)
+            top1, top5 = knn(trf, trl, tef, tel, k, T, nc)
+            out.append(dict(seed=seed, n_train=ntr, n_test=nte, dim=dim, num_classes=nc, noise=noise, k=k, T=T,
+                            top1=top1, top5=top5))
+            print("knn", out[-1])
+    finally:
+        torch.Tensor.cuda = orig
+    json.dump(out, open(os.path.join(GOLD, "knn.json"), "w"))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["backbone", "head", "windows", "selection", "driver", "attn"]
+    what = sys.argv[1:] or ["backbone", "head", "windows", "selection", "driver", "attn", "knn"]
     models = gen_backbone() if ("backbone" in what or "head" in what) else None
     if "head" in what:
         gen_head_loss(models)
@@ -235,3 +265,5 @@ if __name__ == "__main__":
         gen_driver(models)
     if "attn" in what:
         gen_attn()
+    if "knn" in what:
+        gen_knn()

@@ -85,3 +85,19 @@ def load():
                    get_vit_base_patch16_224=tsf.get_vit_base_patch16_224, VisionTransformer=tsf.VisionTransformer,
                    DINOHead=vt.DINOHead, DINOLoss=ds.DINOLoss, export_loss=ds.export_loss)
     return _loaded
+
+
+def load_knn_classifier():
+    """The reference's `knn_classifier` (eval_knn.py:138-178) compiled from its own source text.  eval_knn.py cannot be
+    imported as a module (kornia / fvcore dependent dataset imports at the top), so the function definition is cut out
+    with `ast` and executed unmodified in a namespace that holds only `torch`."""
+    import ast
+    import torch
+    path = os.path.join(REF_ROOT, "eval_knn.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "knn_classifier")
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ns = {"torch": torch}
+    exec(compile(mod, path, "exec"), ns)
+    return ns["knn_classifier"]

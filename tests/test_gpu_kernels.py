@@ -227,3 +227,61 @@ def test_fused_uint8_preprocess_is_bit_exact(dev):
         got = preprocess_frames(raw.to(dev), rate, crop_size=crop)
         assert got.is_cuda and tuple(got.shape) == tuple(ref.shape)
         assert torch.equal(got.cpu(), ref)
+
+
+# ---- weighted k-NN evaluation (eval_knn.py:138-178) ----------------------------------------------------------------
+def test_knn_similarity_topk_vote_vs_oracle(dev):
+    import json
+    import os
+    import dvst_oracle as O
+    from dvst_b200.eval_knn import knn_classifier, knn_classifier_multi, knn_topk, knn_vote
+    from dvst_b200.testing import synth_knn_features
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "knn.json")))
+    for c in cases:
+        trf, trl, tef, tel = synth_knn_features(c["seed"], c["n_train"], c["n_test"], c["dim"], c["num_classes"],
+                                                c["noise"])
+        top1, top5, rank, idx = O.knn_classifier(trf, trl, tef, tel, c["k"], c["T"], c["num_classes"])
+        d, i = knn_topk(trf.to(dev), tef.to(dev), c["k"], rows_per_chunk=128)  # several similarity slabs
+        sim = tef @ trf.t()
+        # neighbour lists identical except where two fp32 similarities are closer than summation-order noise
+        il = i.cpu().long()
+        diff = il != idx
+        assert diff.float().mean() < 0.01
+        assert (torch.gather(sim, 1, il) - torch.gather(sim, 1, idx)).abs()[diff].sum() <= 2e-6 * max(int(diff.sum()), 1)
+        assert (d.cpu() - torch.gather(sim, 1, i.cpu().long())).abs().max() < 2e-6
+        assert (d[:, :-1] >= d[:, 1:]).all()
+        r, pred = knn_vote(d, i, trl.to(dev), tel.to(dev), c["k"], c["T"], c["num_classes"], return_predictions=True)
+        assert (r.cpu().long() == rank).float().mean() > 0.99
+        got = knn_classifier(trf.to(dev), trl.to(dev), tef.to(dev), tel.to(dev), c["k"], c["T"], c["num_classes"])
+        step = 100.0 / c["n_test"]
+        # the reference's own numbers (golden) within one test sample
+        assert abs(got[0] - c["top1"]) <= step + 1e-9 and abs(got[1] - c["top5"]) <= step + 1e-9, (c, got)
+    # one top-k pass serves every k (prefix property) and equals the per-k calls
+    trf, trl, tef, tel = [t.to(dev) for t in synth_knn_features(2, 1500, 300, 768, 101, 6.0)]
+    multi = knn_classifier_multi(trf, trl, tef, tel, [10, 20, 100, 200], 0.07, 101)
+    for k in (10, 200):
+        assert multi[k] == knn_classifier(trf, trl, tef, tel, k, 0.07, 101)
+
+
+def test_knn_topk_ties_and_edges(dev):
+    """Equal similarities are taken in ascending index order (duplicated train rows); k = n_train; k = 1."""
+    from dvst_b200.eval_knn import knn_topk
+    g = torch.Generator().manual_seed(0)
+    base = torch.nn.functional.normalize(torch.randn(40, 32, generator=g), dim=1)
+    train = base.repeat(8, 1)                       # every similarity value appears 8 times: indices j, j+40, ...
+    test = torch.nn.functional.normalize(torch.randn(17, 32, generator=g), dim=1)
+    sim = test @ train.t()
+    ref = torch.sort(sim, dim=1, descending=True, stable=True)
+    for k in (1, 5, 8, 13, 320):
+        d, i = knn_topk(train.to(dev), test.to(dev), k)
+        i = i.cpu().long()
+        # within a group of 8 duplicates the GPU's fp32 sums are identical, so ascending index order must hold
+        assert torch.equal(i % 40, ref.indices[:, :k] % 40)
+        grp = i // 40
+        same = (i[:, 1:] % 40) == (i[:, :-1] % 40)
+        assert (grp[:, 1:][same] > grp[:, :-1][same]).all()
+        assert len(set(i[0].tolist())) == k
+    with pytest.raises(ValueError):
+        knn_topk(train.to(dev), test.to(dev), 321)
+    with pytest.raises(_lib.DvstError):
+        knn_topk(train, test, 3)

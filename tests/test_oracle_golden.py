@@ -113,3 +113,16 @@ def test_center_update_and_train_loss_shapes():
     assert l.ndim == 0 and torch.isfinite(l)
     c2 = O.center_update(c, [t[:B], t[B:]])
     assert torch.allclose(c2, c * 0.9 + t.sum(0, keepdim=True) / (B * 2) * 0.1, atol=1e-6)
+
+
+def test_knn_classifier_matches_reference(golden_dir):
+    """oracle knn_classifier against the reference's own knn_classifier outputs (eval_knn.py:138-178)."""
+    from dvst_b200.testing import synth_knn_features
+    cases = json.load(open(os.path.join(golden_dir, "knn.json")))
+    assert len(cases) >= 6
+    for c in cases:
+        trf, trl, tef, tel = synth_knn_features(c["seed"], c["n_train"], c["n_test"], c["dim"], c["num_classes"],
+                                                c["noise"])
+        top1, top5, rank, idx = O.knn_classifier(trf, trl, tef, tel, c["k"], c["T"], c["num_classes"])
+        assert abs(top1 - c["top1"]) < 1e-9 and abs(top5 - c["top5"]) < 1e-9, c
+        assert idx.shape == (c["n_test"], c["k"]) and rank.shape == (c["n_test"],)

@@ -62,3 +62,19 @@ def test_head_and_loss_fp64():
         lref = torch.stack([L(ref[k], ref[(k + 1) % 3]) for k in range(3)])
     lgot = O.dino_pair_loss(got, got.roll(-1, 0), torch.zeros(1, 1024, dtype=torch.float64), 0.04, 0.1)
     assert (lgot - lref).abs().max().item() < 1e-10
+
+
+def test_knn_classifier_live():
+    """oracle knn_classifier vs the reference function compiled from its own source (eval_knn.py:138-178)."""
+    from dvst_b200.testing import synth_knn_features
+    knn = ref_shim.load_knn_classifier()
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for seed, k, nc in ((11, 7, 9), (12, 30, 25)):
+            trf, trl, tef, tel = synth_knn_features(seed, 500, 200, 48, nc, 3.0)
+            ref = knn(trf, trl, tef, tel, k, 0.07, nc)
+            got = O.knn_classifier(trf, trl, tef, tel, k, 0.07, nc)
+            assert abs(got[0] - ref[0]) < 1e-9 and abs(got[1] - ref[1]) < 1e-9
+    finally:
+        torch.Tensor.cuda = orig
