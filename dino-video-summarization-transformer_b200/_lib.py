@@ -30,6 +30,7 @@ SIGNATURES = {
     "dvst_set_gemm_cta_group": (None, [c_int]),
     "dvst_set_attention_impl": (None, [c_int]),
     "dvst_set_chunk_rows": (None, [c_ll]),
+    "dvst_set_ln_fusion": (None, [c_int]),
     "dvst_profile_enable": (None, [c_int]),
     "dvst_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "dvst_create": (c_int, [c_void_p, c_void_p]),
@@ -58,6 +59,9 @@ SIGNATURES = {
                                   c_void_p]),
     "dvst_select_frames": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dvst_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dvst_rowstats768": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p]),
+    "dvst_gemm_bf16_ln": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_float, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "dvst_knn_similarity": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "dvst_knn_topk": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "dvst_knn_vote": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p,
@@ -78,6 +82,9 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        # experiment switches (A/B runs of bench.py on one box): DVST_LN_FUSION=0 forces the stand-alone LayerNorm
+        if os.environ.get("DVST_LN_FUSION") == "0":
+            l.dvst_set_ln_fusion(0)
         _lib = l
     return _lib
 

@@ -167,6 +167,32 @@ int dvst_preprocess_u8(const unsigned char* video, int n_frames, int H, int W, i
                               static_cast<cudaStream_t>(stream));
 }
 
+int dvst_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M, void* stream) {
+  if (x == nullptr || xb == nullptr || stats == nullptr) return set_error("dvst_rowstats768: null argument");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (ldx % 4) || (reinterpret_cast<uintptr_t>(xb) & 7) || (ldxb % 4) ||
+      (reinterpret_cast<uintptr_t>(stats) & 7))
+    return set_error("dvst_rowstats768: misaligned argument");
+  return launch_rowstats768(x, ldx, xb, ldxb, stats, M, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
+                      const float* ln_stats, const float* ln_colsum, float ln_eps, float* x_inout, long long ldx,
+                      void* xb, long long ldxb, float* stats_out, void* out, long long ldo, int act, void* stream) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.M = M; g.N = N; g.K = K;
+  g.act = act;
+  if (x_inout != nullptr) {
+    if (ln_stats != nullptr) return set_error("dvst_gemm_bf16_ln: choose the consumer (ln_stats) or the producer (x_inout) form");
+    g.residual = x_inout; g.ldr = ldx; g.out = x_inout; g.ldo = ldx; g.out_kind = 3;
+    g.xb = xb; g.ldxb = ldxb; g.stats_out = stats_out;
+  } else {
+    if (ln_stats == nullptr) return set_error("dvst_gemm_bf16_ln: neither ln_stats nor x_inout given");
+    g.out = out; g.ldo = ldo; g.out_kind = 0;
+    g.ln_stats = ln_stats; g.ln_colsum = ln_colsum; g.ln_eps = ln_eps;
+  }
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
 int dvst_knn_similarity(const float* test, long long ldt, const float* train, long long ldr, int n_test, int n_train,
                         int dim, float* sim, long long lds, void* stream) {
   if (test == nullptr || train == nullptr || sim == nullptr) return set_error("dvst_knn_similarity: null argument");

@@ -33,8 +33,16 @@ struct GemmArgs {
   long long ldr = 0;
   void* out = nullptr;
   long long ldo = 0;
-  int out_kind = 0;  // 0 bf16, 1 fp32, 2 bf16 hi/lo pair
+  int out_kind = 0;  // 0 bf16, 1 fp32, 2 bf16 hi/lo pair, 3 fp32 in-place residual + bf16 copy `xb` + row stats
   long long lo_off = 0;
+  // deferred LayerNorm (gemm_sm100.cu): consumer side (out_kind 0, K = 768) ...
+  const float* ln_stats = nullptr;   // fp32 [M, 6, 2] per-128-column (sum, sumsq) of the row A was cast from
+  const float* ln_colsum = nullptr;  // fp32 [N] row sums of the gamma-folded bf16 weight
+  float ln_eps = 1e-6f;
+  // ... and producer side (out_kind 3, N = 768)
+  void* xb = nullptr;                // bf16 [M, ldxb]
+  long long ldxb = 0;
+  float* stats_out = nullptr;        // fp32 [M, N / 128, 2]
   int act = 0;  // 0 none, 1 GELU(erf)
   int M = 0, N = 0, K = 0;
   int split = 0;
@@ -45,6 +53,10 @@ void set_gemm_cta_group(int cg);  // 1 or 2 (default 2); tuning / test hook
 int launch_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
                         long long ldo, int out_kind, long long lo_off, long long M, float eps, cudaStream_t st,
                         long long rm_group = 0, long long rm_stride = 0, long long rm_offset = 0);
+// xb = bf16(x), stats[row][j] = (sum, sumsq) of columns [128 j, 128 j + 128): the deferred-LayerNorm inputs for rows that
+// no residual GEMM has written yet (CLS rows after embedding).
+int launch_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M,
+                       cudaStream_t st);
 int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,
                     const int* starts, cudaStream_t st);
 int launch_cast_bf16(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off, long long M,

@@ -80,6 +80,27 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restri
   }
 }
 
+// Deferred-LayerNorm inputs for rows not produced by a residual GEMM: xb = bf16(x), per-128-column (sum, sumsq).
+__global__ void __launch_bounds__(256) rowstats768_kernel(const float* __restrict__ x, long long ldx,
+                                                          __nv_bfloat16* __restrict__ xb, long long ldxb,
+                                                          float* __restrict__ stats, long long M) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {  // one partial per 128 columns = one float4 per lane
+    const int c4 = j * 32 + lane;
+    const float4 v = xr[c4];
+    float s1 = (v.x + v.y) + (v.z + v.w);
+    float s2 = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    *reinterpret_cast<uint2*>(xb + row * ldxb + c4 * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + (row * 6 + j) * 2) = make_float2(s1, s2);
+  }
+}
+
 // im2col for Conv2d(k=16, s=16) (PatchEmbed, timesformer.py:201-208): x [B,3,T,H,W] fp32 -> rows (b, n, t) in the
 // resident token order, 768 columns in (c, ky, kx) order = the flattened conv weight's K order.
 // One thread moves 8 consecutive kx (two float4 loads, one 16-byte bf16 store).
@@ -310,6 +331,16 @@ int launch_layernorm768(const float* x, long long ldx, const float* gamma, const
                                             rm_stride, rm_offset);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("layernorm launch failed");
+}
+
+int launch_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M,
+                       cudaStream_t st) {
+  if (M <= 0) return 0;
+  ProfScope prof(PROF_LAYERNORM, static_cast<double>(M) * D * 6.0, st);
+  rowstats768_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(xb), ldxb,
+                                                                        stats, M);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("rowstats launch failed");
 }
 
 int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,

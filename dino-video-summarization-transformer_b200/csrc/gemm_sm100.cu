@@ -15,6 +15,12 @@
 //   warps 4..11 : epilogue                      - tcgen05.ld 32x32b.x32 -> bias / GELU / dtype -> swizzled smem box ->
 //                                                 TMA store (bf16, fp32, hi/lo pair) or TMA reduce-add (fused residual)
 //
+// Deferred LayerNorm (bf16 precision): a residual GEMM (kOut = 3) reads the fp32 residual tile through TMA, adds,
+// stores the new fp32 stream AND its bf16 copy `xb`, and leaves per-row partial (sum, sum of squares) of the new row in
+// `stats[row][128-column block]`; the GEMM that consumes LayerNorm(x) (kLN = 1) then runs on `xb` with gamma folded into W:
+//   LN(x) W^T + b = rstd_r (xb W'^T)[r,c] - rstd_r mean_r colsum(W')[c] + (b + W beta)[c],   W' = bf16(gamma * W)
+// so the stand-alone LayerNorm pass (read 4 B + write 2 B per element) disappears from the block.
+//
 // `split` mode: A and W hold [hi | lo] bf16 halves along K (lo at column offset K); the K loop then runs the three
 // products hi*hi, hi*lo, lo*hi into the same accumulator (~16 mantissa bits) - the "precision=high" path that
 // reference-exact scoring (dino_similarity.py:59-63, tau_t = 0.02) needs.
@@ -48,7 +54,8 @@ template <int kCG> struct Cfg {
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = kCG == 1 ? 3 : 5;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 256;
+  static constexpr int EPI_BYTES = EPI_WARPS * STG_BYTES;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + 256;
 };
 
 struct GemmParams {
@@ -60,6 +67,10 @@ struct GemmParams {
   int lo_off;
   int act;  // 0 = none, 1 = exact-erf GELU
   int num_m_blocks, num_n_blocks;  // in units of (kCG * 128) x 256 tiles
+  const float* ln_stats;   // kLN: fp32 [M, 6, 2] per-128-column (sum, sumsq) of the 768-wide fp32 row A was cast from
+  const float* ln_colsum;  // kLN: fp32 [N] row sums of the (gamma-folded, bf16-rounded) weight
+  float ln_eps;
+  float* stats_out;        // producers: fp32 [M, N / 128, 2]
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) (nn.GELU default, timesformer.py:37).  erf via Abramowitz-Stegun 7.1.26
@@ -109,10 +120,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 
 // kOut: 0 = bf16, 1 = fp32 (plain or reduce-add), 2 = bf16 hi/lo pair.  kAct: 0 = none, 1 = exact-erf GELU.  Compile-time
 // so the epilogue (issue-bound next to the 256x256x768 MMA of fc1) carries no predicated code of the other modes.
-template <int kCG, int kOut, int kAct>
+// kOut = 3: fp32 in-place residual (TMA load + add + TMA store) + bf16 copy + row statistics (deferred LayerNorm producer).
+// kLN = 1: deferred LayerNorm consumer (bf16 output only).
+template <int kCG, int kOut, int kAct, int kLN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmXb,
+                    const GemmParams p) {
+  constexpr int EW = kOut == 3 ? 4 : EPI_WARPS;  // epilogue warps that take part
+  constexpr bool kProducer = kOut == 3;
   using C = Cfg<kCG>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -123,12 +139,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t sA = base;
   const uint32_t sB = base + STAGES * A_BYTES;
   const uint32_t stg_all = base + STAGES * C::STAGE_BYTES;  // 1024-byte aligned
-  const uint32_t bars = base + STAGES * C::STAGE_BYTES + EPI_WARPS * STG_BYTES;
+  const uint32_t bars = base + STAGES * C::STAGE_BYTES + C::EPI_BYTES;
   const uint32_t full_bar = bars;                       // [STAGES]   (2-CTA: only the leader's copy is used)
   const uint32_t empty_bar = bars + 8 * STAGES;         // [STAGES]
   const uint32_t tfull_bar = bars + 16 * STAGES;        // [ACC_STAGES]
   const uint32_t tempty_bar = tfull_bar + 8 * ACC_STAGES;  // (2-CTA: only the leader's copy is used)
   const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
+  const uint32_t res_bar = tmem_slot + 8;                // producers: [EW warps][3 ring slots]
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5;
@@ -140,6 +157,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
+    if constexpr (kProducer) tma_prefetch_desc(&tmXb);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -148,7 +166,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, EPI_WARPS * kCG);
+      mbar_init(tempty_bar + 8 * a, EW * kCG);
+    }
+    if constexpr (kProducer) {
+      for (int i = 0; i < 3 * EW; ++i) mbar_init(res_bar + 8 * i, 1);
     }
     fence_mbar_init();
   }
@@ -264,10 +285,137 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       buf = (buf + 1) % STG_BUFS;
     };
 
+    if constexpr (kProducer) {
+      // ---- deferred-LayerNorm producer: x <- x + acc + bias (fp32, in place), xb <- bf16(x), stats <- row partials.
+      // 4 warps; warp e owns rows q*32.. of the tile and walks its 256 columns in 8 chunks of 32.  Per warp: a ring of
+      // three 4 KiB boxes (TMA load of the residual chunk -> add in place -> TMA store from the same box) and two 2 KiB
+      // bf16 boxes (SWIZZLE_64B).  Residual loads run two chunks ahead, across tile boundaries.  One (sum, sumsq)
+      // partial per 128 columns.  (Measured and dropped: 8 warps x 4 chunks with 3 operand stages for the K = 768
+      // producers - twice the residual bytes in flight - gave the same step time, 54.14 vs 54.16 ms.)
+      constexpr int NCH = 8;
+      constexpr int col_base = 0;
+      if (e < EW) {
+        const uint32_t ring = stg_all + e * (2 * STG_BYTES);
+        const uint32_t bst = ring + 3 * STG_BUF_BYTES;
+        const uint32_t rbar = res_bar + e * 24;
+        const uint32_t brow_off = lane * 64;
+        const int bsw = (lane >> 1) & 3;
+        int l_tile = tile0, l_c = 0;
+        uint32_t l_g = 0;
+        auto issue_load = [&]() {  // lane 0 only
+          if (l_tile < num_tiles) {
+            const int lm = l_tile / p.num_n_blocks, ln = l_tile % p.num_n_blocks;
+            const uint32_t sl = l_g % 3;
+            mbar_arrive_expect_tx(rbar + 8 * sl, STG_BUF_BYTES);
+            tma_load_2d(ring + sl * STG_BUF_BYTES, &tmO, rbar + 8 * sl, ln * BN + col_base + l_c * 32,
+                        (lm * kCG + static_cast<int>(cta_rank)) * BM + q * 32);
+            ++l_g;
+            if (++l_c == NCH) { l_c = 0; l_tile += tile_step; }
+          }
+        };
+        if (lane == 0) { issue_load(); issue_load(); }
+        uint32_t g = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+          const int m_blk = tile / p.num_n_blocks;
+          const int n_blk = tile % p.num_n_blocks;
+          const int grow = (m_blk * kCG + cta_rank) * BM + q * 32;
+          mbar_wait(tfull_bar + 8 * a, aph);
+          tc_fence_after();
+          const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col_base;
+          uint32_t v[32];
+          tmem_ld_32x32(trow, v);
+          float s1 = 0.f, s2 = 0.f;
+          float2* stat_row = reinterpret_cast<float2*>(p.stats_out) +
+                             (static_cast<long long>(grow + lane) * (2 * p.num_n_blocks) + 2 * n_blk + (col_base >> 7));
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c, ++g) {
+            const int gcol0 = n_blk * BN + col_base + c * 32;
+            const uint32_t sl = g % 3;
+            mbar_wait(rbar + 8 * sl, (g / 3) & 1);
+            tmem_ld_wait();
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
+            if (c < NCH - 1) tmem_ld_32x32(trow + (c + 1) * 32, v);
+            else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (kCG == 1 || leader) mbar_arrive(tempty_bar + 8 * a);
+                else mbar_arrive_cluster(tempty_bar + 8 * a, 0);
+              }
+            }
+            const uint32_t box = ring + sl * STG_BUF_BYTES + row_off;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t addr = box + ((j ^ sw) << 4);
+              float4 r4;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w)
+                           : "r"(addr) : "memory");
+              const float4 b4 = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol0) + j)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+              w[4 * j] = (w[4 * j] + b4.x) + r4.x;
+              w[4 * j + 1] = (w[4 * j + 1] + b4.y) + r4.y;
+              w[4 * j + 2] = (w[4 * j + 2] + b4.z) + r4.z;
+              w[4 * j + 3] = (w[4 * j + 3] + b4.w) + r4.w;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(w[4 * j]), "f"(w[4 * j + 1]),
+                           "f"(w[4 * j + 2]), "f"(w[4 * j + 3]) : "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              s1 += w[j];
+              s2 = fmaf(w[j], w[j], s2);
+            }
+            const uint32_t bbox = bst + (g & 1) * (STG_BUF_BYTES / 2) + brow_off;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bbox + ((j ^ bsw) << 4)),
+                           "r"(pack_bf16x2(w[8 * j], w[8 * j + 1])), "r"(pack_bf16x2(w[8 * j + 2], w[8 * j + 3])),
+                           "r"(pack_bf16x2(w[8 * j + 4], w[8 * j + 5])), "r"(pack_bf16x2(w[8 * j + 6], w[8 * j + 7]))
+                           : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(ring + sl * STG_BUF_BYTES), "r"(gcol0), "r"(grow)
+                           : "memory");
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmXb)), "r"(bst + (g & 1) * (STG_BUF_BYTES / 2)), "r"(gcol0),
+                             "r"(grow) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              // the stores of the previous chunk have finished reading their boxes: its ring slot takes the load that
+              // runs two chunks ahead, its bf16 box is the next chunk's
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              issue_load();
+            }
+            __syncwarp();
+            if ((c & 3) == 3) {  // 128 columns done: one partial
+              if (grow + lane < p.M) stat_row[c >> 2] = make_float2(s1, s2);
+              s1 = 0.f;
+              s2 = 0.f;
+            }
+          }
+          if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+    } else {
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile % p.num_n_blocks;
       const int grow = (m_blk * kCG + cta_rank) * BM + q * 32;
+      float ln_rstd = 0.f, ln_nmr = 0.f;  // deferred LayerNorm: rstd and -rstd * mean of this thread's row
+      if constexpr (kLN == 1) {
+        if (grow + lane < p.M) {
+          const float4* sp = reinterpret_cast<const float4*>(p.ln_stats) + static_cast<long long>(grow + lane) * 3;
+          const float4 a0 = __ldg(sp), a1 = __ldg(sp + 1), a2 = __ldg(sp + 2);  // 6 x (sum, sumsq) per 128 columns
+          const float mean = (((a0.x + a0.z) + (a1.x + a1.z)) + (a2.x + a2.z)) * (1.0f / 768.0f);
+          const float var = (((a0.y + a0.w) + (a1.y + a1.w)) + (a2.y + a2.w)) * (1.0f / 768.0f) - mean * mean;
+          ln_rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+          ln_nmr = -ln_rstd * mean;
+        }
+      }
       mbar_wait(tfull_bar + 8 * a, aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * 128;
@@ -336,7 +484,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j4 = 0; j4 < 8; ++j4) {  // branch-free: a null bias adds zeros
               const float4 b4 = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + hh * 32) + j4)
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-              f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
+              if constexpr (kLN == 1) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + gcol0 + hh * 32) + j4);
+                f[4 * j4] = fmaf(ln_rstd, f[4 * j4], fmaf(ln_nmr, s4.x, b4.x));
+                f[4 * j4 + 1] = fmaf(ln_rstd, f[4 * j4 + 1], fmaf(ln_nmr, s4.y, b4.y));
+                f[4 * j4 + 2] = fmaf(ln_rstd, f[4 * j4 + 2], fmaf(ln_nmr, s4.z, b4.z));
+                f[4 * j4 + 3] = fmaf(ln_rstd, f[4 * j4 + 3], fmaf(ln_nmr, s4.w, b4.w));
+              } else {
+                f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
+              }
             }
             if constexpr (kAct == 1) {
 #pragma unroll
@@ -360,6 +516,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
+    }  // not a producer
   }
 
   tc_fence_before();
@@ -393,7 +550,7 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                 uint32_t box_rows, uint32_t box_cols) {
+                 uint32_t box_rows, uint32_t box_cols, bool swizzle64 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error("cuTensorMapEncodeTiled entry point not found");
   cuuint64_t gdim[2] = {cols, rows};
@@ -402,8 +559,8 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t row
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (code %d)", static_cast<int>(r));
   return 0;
 }
@@ -441,13 +598,13 @@ int num_sms() {
 static int g_gemm_cta_group = 2;
 void set_gemm_cta_group(int cg) { g_gemm_cta_group = cg == 1 ? 1 : 2; }
 
-template <int kCG, int kOut, int kAct>
+template <int kCG, int kOut, int kAct, int kLN>
 static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   using C = Cfg<kCG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kCG, kOut, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kCG, kOut, kAct, kLN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -456,8 +613,11 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, kcols, g.lda, BM, BK)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmB, g.W, g.N, kcols, g.ldw, C::B_ROWS, BK)) return rc;
   const uint64_t out_cols = g.out_kind == 2 ? static_cast<uint64_t>(g.lo_off) + g.N : g.N;
-  if (int rc = make_tmap_2d(&tmO, g.out, g.out_kind == 1 ? 4 : 2, g.M, out_cols, g.ldo, 32, g.out_kind == 1 ? 32 : 64))
-    return rc;
+  const bool f32out = g.out_kind == 1 || g.out_kind == 3;
+  if (int rc = make_tmap_2d(&tmO, g.out, f32out ? 4 : 2, g.M, out_cols, g.ldo, 32, f32out ? 32 : 64)) return rc;
+  CUtensorMap tmXb = tmO;
+  if (kOut == 3)
+    if (int rc = make_tmap_2d(&tmXb, g.xb, 2, g.M, g.N, g.ldxb, 32, 32, true)) return rc;
 
   GemmParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.split = g.split;
@@ -465,6 +625,7 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   p.out_kind = g.out_kind; p.lo_off = static_cast<int>(g.lo_off); p.act = g.act;
   p.num_m_blocks = (g.M + BM * kCG - 1) / (BM * kCG);
   p.num_n_blocks = g.N / BN;
+  p.ln_stats = g.ln_stats; p.ln_colsum = g.ln_colsum; p.ln_eps = g.ln_eps; p.stats_out = g.stats_out;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_units = num_sms() / kCG;
   const int units = tiles < max_units ? tiles : max_units;
@@ -482,7 +643,7 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(PROF_GEMM, 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG, kOut, kAct>, tmA, tmB, tmO, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG, kOut, kAct, kLN>, tmA, tmB, tmO, tmXb, p);
   if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -495,18 +656,36 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15) || (g.lda % 8) ||
       (g.ldw % 8))
     return set_error("gemm: operands must be 16-byte aligned with leading dimensions multiple of 8");
-  if (g.out_kind < 0 || g.out_kind > 2) return set_error("gemm: bad out_kind %d", g.out_kind);
-  if ((reinterpret_cast<uintptr_t>(g.out) & 15) || (g.ldo % (g.out_kind == 1 ? 4 : 8)) || (g.lo_off % 8))
+  if (g.out_kind < 0 || g.out_kind > 3) return set_error("gemm: bad out_kind %d", g.out_kind);
+  const bool f32out = g.out_kind == 1 || g.out_kind == 3;
+  if ((reinterpret_cast<uintptr_t>(g.out) & 15) || (g.ldo % (f32out ? 4 : 8)) || (g.lo_off % 8))
     return set_error("gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
-  if (g.residual != nullptr && (g.residual != g.out || g.out_kind != 1 || g.ldr != g.ldo))
+  if (g.residual != nullptr && (g.residual != g.out || !f32out || g.ldr != g.ldo))
     return set_error("gemm: the fused residual add is in place (residual must alias the fp32 output)");
+  if (g.out_kind == 3) {
+    // deferred-LayerNorm producer: x += A W^T + b in place, xb = bf16(x), stats[row][n_block] = (sum, sumsq)
+    if (g.residual == nullptr || g.xb == nullptr || g.stats_out == nullptr || g.act != 0 || g.split != 0)
+      return set_error("gemm: out_kind 3 needs residual (in place), xb, stats_out, no activation, bf16 precision");
+    if ((reinterpret_cast<uintptr_t>(g.xb) & 15) || (g.ldxb % 8) || (reinterpret_cast<uintptr_t>(g.stats_out) & 15))
+      return set_error("gemm: xb and stats must be 16-byte aligned, ldxb a multiple of 8");
+  }
+  if (g.ln_stats != nullptr) {
+    if (g.out_kind != 0 || g.K != 768 || g.ln_colsum == nullptr || g.split != 0 ||
+        (reinterpret_cast<uintptr_t>(g.ln_stats) & 15) || (reinterpret_cast<uintptr_t>(g.ln_colsum) & 15))
+      return set_error("gemm: deferred LayerNorm needs bf16 output, K = 768, a column-sum vector, bf16 precision");
+  }
   // small problems (fewer 256-row tiles than SM pairs would leave half the chip idle) stay on the 1-CTA kernel
   const long long tiles2 = static_cast<long long>((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   if (g.act < 0 || g.act > 1) return set_error("gemm: bad act %d", g.act);
   const bool cg2 = g_gemm_cta_group == 2 && tiles2 >= num_sms() / 2;
+  if (g.ln_stats != nullptr) {
+    if (g.act == 0) return cg2 ? launch_gemm_impl<2, 0, 0, 1>(g, stream) : launch_gemm_impl<1, 0, 0, 1>(g, stream);
+    return cg2 ? launch_gemm_impl<2, 0, 1, 1>(g, stream) : launch_gemm_impl<1, 0, 1, 1>(g, stream);
+  }
+  if (g.out_kind == 3) return cg2 ? launch_gemm_impl<2, 3, 0, 0>(g, stream) : launch_gemm_impl<1, 3, 0, 0>(g, stream);
 #define DVST_GEMM_CASE(OUT, ACT)                                                                   \
   if (g.out_kind == OUT && g.act == ACT)                                                           \
-    return cg2 ? launch_gemm_impl<2, OUT, ACT>(g, stream) : launch_gemm_impl<1, OUT, ACT>(g, stream);
+    return cg2 ? launch_gemm_impl<2, OUT, ACT, 0>(g, stream) : launch_gemm_impl<1, OUT, ACT, 0>(g, stream);
   DVST_GEMM_CASE(0, 0)
   DVST_GEMM_CASE(0, 1)
   DVST_GEMM_CASE(1, 0)

@@ -34,12 +34,18 @@ struct BlockW {
              *fc2_w = nullptr;
   const float *tqkv_b = nullptr, *tproj_b = nullptr, *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr,
               *fc2_b = nullptr;
+  // deferred LayerNorm (optional, bf16 precision): W' = bf16(gamma * W), colsum(W'), b + W beta for the three Linears
+  // that consume a LayerNorm output (temporal qkv <- temporal_norm1, qkv <- norm1, fc1 <- norm2)
+  const void *tqkv_wf = nullptr, *qkv_wf = nullptr, *fc1_wf = nullptr;
+  const float *tqkv_sf = nullptr, *tqkv_bf = nullptr, *qkv_sf = nullptr, *qkv_bf = nullptr, *fc1_sf = nullptr,
+              *fc1_bf = nullptr;
 };
 
 struct Model {
   dvst_config cfg;
   std::unordered_map<std::string, const void*> named;
   bool finalized = false;
+  bool fused_ln = false;  // every block carries the folded tensors
   const void* pe_w = nullptr;
   const float *pe_b = nullptr, *cls_pos0 = nullptr, *pos = nullptr, *time_embed = nullptr, *norm_w = nullptr,
               *norm_b = nullptr;
@@ -54,6 +60,8 @@ struct Workspace {
   float* cls_acc;
   float* emb;
   float* tmp;  // [rows, 768] fp32 scratch for space_only's frame mean
+  void* xb;     // bf16 [M, 768] copy of x (deferred LayerNorm: the A operand of the consuming GEMM)
+  float* stats; // fp32 [M, 6, 2] per-128-column (sum, sumsq) of every row of x
   size_t total;
 };
 
@@ -78,6 +86,9 @@ static Workspace carve(const Model& m, void* base, long long B, int T, int gh, i
   w.emb = static_cast<float*>(take(static_cast<size_t>(N) * T * D * 4));
   w.tmp = static_cast<float*>(take(m.cfg.attention_type == DVST_ATTN_SPACE_ONLY
                                        ? static_cast<size_t>(B) * (N + 1) * D * 4 : 1024));
+  const bool fl = m.fused_ln && m.cfg.precision == DVST_PRECISION_BF16;
+  w.xb = take(fl ? static_cast<size_t>(M) * D * 2 : 1024);
+  w.stats = static_cast<float*>(take(fl ? static_cast<size_t>(M) * 12 * 4 : 1024));
   w.total = off;
   return w;
 }
@@ -149,12 +160,38 @@ int dvst_finalize_weights(dvst_model* h) {
     b.fc2_w = get(p + "mlp.fc2.w"); b.fc2_b = getf(p + "mlp.fc2.b");
   }
   if (!missing.empty()) return set_error("dvst_finalize_weights: missing tensors: %s", missing.c_str());
+  // optional folded tensors of the deferred LayerNorm
+  auto opt = [&](const std::string& k) -> const void* {
+    auto it = m->named.find(k);
+    return it == m->named.end() ? nullptr : it->second;
+  };
+  bool all = m->cfg.precision == DVST_PRECISION_BF16;
+  for (int i = 0; i < m->cfg.depth; ++i) {
+    const std::string p = "blocks." + std::to_string(i) + ".";
+    BlockW& b = m->blocks[i];
+    if (divided) {
+      b.tqkv_wf = opt(p + "temporal_attn.qkv.wf");
+      b.tqkv_sf = static_cast<const float*>(opt(p + "temporal_attn.qkv.sf"));
+      b.tqkv_bf = static_cast<const float*>(opt(p + "temporal_attn.qkv.bf"));
+      all = all && b.tqkv_wf && b.tqkv_sf && b.tqkv_bf;
+    }
+    b.qkv_wf = opt(p + "attn.qkv.wf");
+    b.qkv_sf = static_cast<const float*>(opt(p + "attn.qkv.sf"));
+    b.qkv_bf = static_cast<const float*>(opt(p + "attn.qkv.bf"));
+    b.fc1_wf = opt(p + "mlp.fc1.wf");
+    b.fc1_sf = static_cast<const float*>(opt(p + "mlp.fc1.sf"));
+    b.fc1_bf = static_cast<const float*>(opt(p + "mlp.fc1.bf"));
+    all = all && b.qkv_wf && b.qkv_sf && b.qkv_bf && b.fc1_wf && b.fc1_sf && b.fc1_bf;
+  }
+  m->fused_ln = all;
   m->finalized = true;
   return 0;
 }
 
 // Clips per pass: the batch is walked in chunks of about g_chunk_rows token rows so that the activations of one chunk
 // (x, a, qkv, hid) stay resident in the 126 MB L2 between producer and consumer kernels; 0 = whole batch in one pass.
+static int g_ln_fusion = 1;
+void dvst_set_ln_fusion(int on) { g_ln_fusion = on != 0 ? 1 : 0; }
 static long long g_chunk_rows = 0;
 void dvst_set_chunk_rows(long long rows) { g_chunk_rows = rows < 0 ? 0 : rows; }
 static int chunk_clips(int B, long long rows_per_clip) {
@@ -260,30 +297,61 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
   auto ln = [&](const float* src, const float* gw_, const float* gb_, long long rows) {
     return launch_layernorm768(src, D, gw_, gb_, w.a, lda, act_kind, D, rows, LN_EPS, st);
   };
+  // Deferred LayerNorm (bf16 precision, folded tensors present): residual GEMMs also emit xb = bf16(x) and the row
+  // statistics, the GEMMs that consume LayerNorm(x) run on xb with gamma folded into their weights (gemm_sm100.cu).
+  const bool fl = m->fused_ln && g_ln_fusion && !split;
+  __nv_bfloat16* xb = static_cast<__nv_bfloat16*>(w.xb);
+  // x[row0 .. row0+rows) += A W^T + bias, plus xb / stats of those rows
+  auto gemm_res = [&](const void* A, const void* Wt, const float* bias, long long row0, long long rows, int K) {
+    GemmArgs g;
+    g.A = A; g.lda = K == D ? lda : ldh; g.W = Wt; g.ldw = K; g.bias = bias;
+    g.M = static_cast<int>(rows); g.N = D; g.K = K;
+    g.residual = w.x + row0 * D; g.ldr = D; g.out = w.x + row0 * D; g.ldo = D; g.out_kind = 3;
+    g.xb = xb + row0 * D; g.ldxb = D; g.stats_out = w.stats + row0 * 12;
+    return launch_gemm(g, st);
+  };
+  // out[row0 .. row0+rows) = act(LayerNorm(x) W^T + b) through the folded form
+  auto gemm_ln = [&](const void* Wf, const float* sf, const float* bf, long long row0, long long rows, int Nn, void* o,
+                     long long ldo, int act) {
+    GemmArgs g;
+    g.A = xb + row0 * D; g.lda = D; g.W = Wf; g.ldw = D; g.bias = bf;
+    g.M = static_cast<int>(rows); g.N = Nn; g.K = D;
+    g.out = o; g.ldo = ldo; g.out_kind = 0; g.act = act;
+    g.ln_stats = w.stats + row0 * 12; g.ln_colsum = sf; g.ln_eps = LN_EPS;
+    return launch_gemm(g, st);
+  };
 
   // ---- patch embedding + positional / temporal embedding (timesformer.py:203-209,287-323) ----
   DVST_TRY(launch_embed_table(m->pos, m->cfg.pos_grid, m->time_embed, m->cfg.num_frames, w.emb, gh, gw, T, st));
   DVST_TRY(launch_im2col16(x_in, w.a, lda, split, D, B, T, H, W, starts, st));
   DVST_TRY(launch_tile_rows768(w.emb, N * T, w.x, Mt, st));  // x[b, n, t] = pos + time; the GEMM accumulates onto it
-  DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.x, w.x, D, 1, 0));
+  if (fl) DVST_TRY(gemm_res(w.a, m->pe_w, m->pe_b, 0, Mt, D));
+  else DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.x, w.x, D, 1, 0));
   DVST_TRY(launch_broadcast_row768(m->cls_pos0, w.x + Mt * D, D, static_cast<int>(n_cls), st));
+  if (fl) DVST_TRY(launch_rowstats768(w.x + Mt * D, D, xb + Mt * D, D, w.stats + Mt * 12, n_cls, st));
 
   for (int i = 0; i < m->cfg.depth; ++i) {
     const BlockW& b = m->blocks[i];
     if (att == DVST_ATTN_DIVIDED) {
       // temporal attention over the T tokens of every (b, n); CLS rows excluded (:127-135)
-      DVST_TRY(ln(w.x, b.tnorm_w, b.tnorm_b, Mt));
-      DVST_TRY(gemm(w.a, lda, b.tqkv_w, b.tqkv_b, Mt, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
+      if (fl) {
+        DVST_TRY(gemm_ln(b.tqkv_wf, b.tqkv_sf, b.tqkv_bf, 0, Mt, 3 * D, w.qkv, ldq, 0));
+      } else {
+        DVST_TRY(ln(w.x, b.tnorm_w, b.tnorm_b, Mt));
+        DVST_TRY(gemm(w.a, lda, b.tqkv_w, b.tqkv_b, Mt, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
+      }
       DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, nullptr, 0, B, T, static_cast<int>(N), Mt, split, st));
       // temporal_fc(proj(.)) folded into one 768x768 GEMM at pack time; residual add fused (:131-135)
-      DVST_TRY(gemm(w.a, lda, b.tproj_w, b.tproj_b, Mt, D, D, w.x, w.x, D, 1, 0));
+      if (fl) DVST_TRY(gemm_res(w.a, b.tproj_w, b.tproj_b, 0, Mt, D));
+      else DVST_TRY(gemm(w.a, lda, b.tproj_w, b.tproj_b, Mt, D, D, w.x, w.x, D, 1, 0));
     }
     // spatial (or joint / per-frame) attention (:120-123,140-181)
     const int mode = att == DVST_ATTN_DIVIDED ? 1 : (att == DVST_ATTN_JOINT ? 2 : 3);
-    DVST_TRY(ln(w.x, b.norm1_w, b.norm1_b, M));
+    if (!fl) DVST_TRY(ln(w.x, b.norm1_w, b.norm1_b, M));
     if (i + 1 == m->cfg.depth && get_all == 2) {
       // get_attn: the last block stops after the spatial q / k and returns softmax(q k^T / 8) (:155-157,325-331)
-      DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
+      if (fl) DVST_TRY(gemm_ln(b.qkv_wf, b.qkv_sf, b.qkv_bf, 0, M, 3 * D, w.qkv, ldq, 0));
+      else DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
       return launch_attention_probs(w.qkv, ldq, out, B, T, static_cast<int>(N), Mt, split, st);
     }
     if (i + 1 == m->cfg.depth && !get_all) {
@@ -294,9 +362,15 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
       const long long wrow = split ? 2LL * D : D;  // elements per weight row
       __nv_bfloat16* qkv_bf = static_cast<__nv_bfloat16*>(w.qkv);
       __nv_bfloat16* a_bf = static_cast<__nv_bfloat16*>(w.a);
-      DVST_TRY(gemm(w.a, lda, static_cast<const __nv_bfloat16*>(b.qkv_w) + D * wrow, b.qkv_b + D, Mt, 2 * D, D, nullptr,
-                    qkv_bf + D, ldq, act_kind, 0));
-      DVST_TRY(gemm(a_bf + Mt * lda, lda, b.qkv_w, b.qkv_b, n_cls, 3 * D, D, nullptr, qkv_bf + Mt * ldq, ldq, act_kind, 0));
+      if (fl) {
+        DVST_TRY(gemm_ln(static_cast<const __nv_bfloat16*>(b.qkv_wf) + D * D, b.qkv_sf + D, b.qkv_bf + D, 0, Mt, 2 * D,
+                         qkv_bf + D, ldq, 0));
+        DVST_TRY(gemm_ln(b.qkv_wf, b.qkv_sf, b.qkv_bf, Mt, n_cls, 3 * D, qkv_bf + Mt * ldq, ldq, 0));
+      } else {
+        DVST_TRY(gemm(w.a, lda, static_cast<const __nv_bfloat16*>(b.qkv_w) + D * wrow, b.qkv_b + D, Mt, 2 * D, D, nullptr,
+                      qkv_bf + D, ldq, act_kind, 0));
+        DVST_TRY(gemm(a_bf + Mt * lda, lda, b.qkv_w, b.qkv_b, n_cls, 3 * D, D, nullptr, qkv_bf + Mt * ldq, ldq, act_kind, 0));
+      }
       DVST_TRY(launch_cls_attention(w.qkv, ldq, w.a, lda, w.cls_acc, mode, B, T, static_cast<int>(N), Mt, split, st));
       if (att == DVST_ATTN_DIVIDED)
         DVST_TRY(launch_cls_mean(w.cls_acc, a_bf + Mt * lda, lda, split, D, B, T, nullptr, st));
@@ -307,15 +381,22 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
       DVST_TRY(gemm(w.hid, ldh, b.fc2_w, b.fc2_b, n_cls, D, 4 * D, x_cls, x_cls, D, 1, 0));
       continue;
     }
-    DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
+    if (fl) DVST_TRY(gemm_ln(b.qkv_wf, b.qkv_sf, b.qkv_bf, 0, M, 3 * D, w.qkv, ldq, 0));
+    else DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
     DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, w.cls_acc, mode, B, T, static_cast<int>(N), Mt, split, st));
     if (att == DVST_ATTN_DIVIDED)
       DVST_TRY(launch_cls_mean(w.cls_acc, static_cast<__nv_bfloat16*>(w.a) + Mt * lda, lda, split, D, B, T, nullptr, st));
-    DVST_TRY(gemm(w.a, lda, b.proj_w, b.proj_b, M, D, D, w.x, w.x, D, 1, 0));
-    // MLP (:184)
-    DVST_TRY(ln(w.x, b.norm2_w, b.norm2_b, M));
-    DVST_TRY(gemm(w.a, lda, b.fc1_w, b.fc1_b, M, 4 * D, D, nullptr, w.hid, ldh, act_kind, 1));
-    DVST_TRY(gemm(w.hid, ldh, b.fc2_w, b.fc2_b, M, D, 4 * D, w.x, w.x, D, 1, 0));
+    if (fl) {
+      DVST_TRY(gemm_res(w.a, b.proj_w, b.proj_b, 0, M, D));
+      // MLP (:184)
+      DVST_TRY(gemm_ln(b.fc1_wf, b.fc1_sf, b.fc1_bf, 0, M, 4 * D, w.hid, ldh, 1));
+      DVST_TRY(gemm_res(w.hid, b.fc2_w, b.fc2_b, 0, M, 4 * D));
+    } else {
+      DVST_TRY(gemm(w.a, lda, b.proj_w, b.proj_b, M, D, D, w.x, w.x, D, 1, 0));
+      DVST_TRY(ln(w.x, b.norm2_w, b.norm2_b, M));
+      DVST_TRY(gemm(w.a, lda, b.fc1_w, b.fc1_b, M, 4 * D, D, nullptr, w.hid, ldh, act_kind, 1));
+      DVST_TRY(gemm(w.hid, ldh, b.fc2_w, b.fc2_b, M, D, 4 * D, w.x, w.x, D, 1, 0));
+    }
   }
 
   // ---- final norm (:338-345) ----

@@ -50,6 +50,10 @@ void dvst_set_gemm_cta_group(int cg);
  * tcgen05 + TMEM kernel; 0 forces the mma.sync kernels for every mode. */
 void dvst_set_attention_impl(int impl);
 
+/* Tuning / test hook: 1 (default) lets bf16-precision models whose folded tensors are registered run the deferred
+ * LayerNorm path (see dvst_gemm_bf16_ln); 0 forces the stand-alone LayerNorm kernel.  Call before dvst_workspace_bytes. */
+void dvst_set_ln_fusion(int on);
+
 /* L2-residency tuning: walk a batch in chunks of about `rows` token rows (0 = whole batch per pass).  Results are
  * bit-identical for any value (rows of every kernel are independent).  Call before dvst_workspace_bytes. */
 void dvst_set_chunk_rows(long long rows);
@@ -70,7 +74,10 @@ void dvst_destroy(dvst_model* m);
  *   blocks.<i>.{temporal_norm1,norm1,norm2}.{w,b}                                   fp32 [768]
  *   blocks.<i>.{temporal_attn.qkv,attn.qkv}.w bf16 [2304, 768*k], .b fp32 [2304]
  *   blocks.<i>.temporal_projfc.w bf16 [768, 768*k] = temporal_fc.weight @ temporal_attn.proj.weight, .b fp32 [768]
- *   blocks.<i>.attn.proj.{w,b}, blocks.<i>.mlp.fc1.{w [3072,768*k], b}, blocks.<i>.mlp.fc2.{w [768,3072*k], b}    */
+ *   blocks.<i>.attn.proj.{w,b}, blocks.<i>.mlp.fc1.{w [3072,768*k], b}, blocks.<i>.mlp.fc2.{w [768,3072*k], b}
+ * Optional (bf16 precision; all of them or none): the deferred-LayerNorm form of the three Linears that follow a norm,
+ *   blocks.<i>.{temporal_attn.qkv,attn.qkv,mlp.fc1}.wf bf16 [N, 768] = bf16(gamma * W), .sf fp32 [N] = row sums of wf,
+ *   .bf fp32 [N] = b + W beta   (gamma / beta of temporal_norm1 / norm1 / norm2 respectively)                       */
 int dvst_set_weight(dvst_model* m, const char* name, const void* dev_ptr);
 int dvst_finalize_weights(dvst_model* m);
 
@@ -141,6 +148,18 @@ int dvst_l2norm_rows(const float* in, long long ldi, void* out, long long ldo, i
 int dvst_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
                    int split, const float* residual, long long ldr, void* out, long long ldo, int out_kind,
                    long long lo_off, int act, void* stream);
+/* Deferred LayerNorm (bf16 precision): the stand-alone LayerNorm pass between a residual add and the next Linear
+ * (models/timesformer.py:127-128,140-141,184) is split between the two GEMMs around it.
+ *   producer form (x_inout != NULL, N = 768): x += A W^T + bias in place (fp32), xb = bf16(x) [M, ldxb],
+ *       stats_out[row][N / 128][2] = (sum, sum of squares) of the new row per 128-column block;
+ *   consumer form (ln_stats != NULL, K = 768): out (bf16) = act(rstd (A W^T) - rstd mean colsum + bias) where A = xb,
+ *       W = bf16(gamma * weight) row-major [N, 768], ln_colsum[c] = sum_k W[c, k], bias = b + weight beta  and
+ *       (mean, rstd) come from ln_stats (eps inside the rsqrt as in nn.LayerNorm).
+ * dvst_rowstats768 produces (xb, stats) for rows that no residual GEMM has written (the CLS rows after embedding). */
+int dvst_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M, void* stream);
+int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
+                      const float* ln_stats, const float* ln_colsum, float ln_eps, float* x_inout, long long ldx,
+                      void* xb, long long ldxb, float* stats_out, void* out, long long ldo, int act, void* stream);
 /* nn.LayerNorm(768, eps) over M rows of fp32 (models/timesformer.py:99,105,112,245).  out_kind as above. */
 int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,
                       int out_kind, long long lo_off, long long M, float eps, void* stream);

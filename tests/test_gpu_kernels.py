@@ -285,3 +285,61 @@ def test_knn_topk_ties_and_edges(dev):
         knn_topk(train.to(dev), test.to(dev), 321)
     with pytest.raises(_lib.DvstError):
         knn_topk(train, test, 3)
+
+
+# ---- deferred LayerNorm: residual GEMM that also emits bf16(x) + row statistics, and the GEMM that consumes them -------
+def _ln_producer(A, W, bias, x):
+    L = _lib.lib()
+    M, K = A.shape
+    xb = torch.empty(M, 768, device=A.device, dtype=torch.bfloat16)
+    stats = torch.zeros(M, 6, 2, device=A.device)
+    _lib.check(L.dvst_gemm_bf16_ln(_lib.ptr(A), A.stride(0), _lib.ptr(W), W.stride(0), _lib.ptr(bias), M, 768, K,
+                                   None, None, 0.0, _lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), None, 0, 0,
+                                   _lib.cur_stream()))
+    return xb, stats
+
+
+@pytest.mark.parametrize("M,K", [(1, 768), (77, 768), (300, 3072), (4099, 768), (40000, 768), (33000, 3072)])
+def test_deferred_layernorm_producer(dev, M, K):
+    torch.manual_seed(M + K)
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(768, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(768, device=dev)
+    x0 = torch.randn(M, 768, device=dev) * 2 + 0.3
+    ref = x0.double() + A.double() @ W.double().t() + bias.double()
+    x = x0.clone()
+    xb, stats = _ln_producer(A, W, bias, x)
+    assert _rel(x, ref) < 1e-5                      # in-place fp32 residual stream
+    assert torch.equal(xb, x.bfloat16())            # the bf16 copy is the rounding of exactly what was stored
+    blocks = x.double().view(M, 6, 128)
+    assert torch.allclose(stats[:, :, 0].double(), blocks.sum(-1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[:, :, 1].double(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,act", [(1, 2304, 0), (130, 3072, 1), (4099, 2304, 0), (40000, 3072, 1), (40000, 1536, 0)])
+def test_deferred_layernorm_consumer(dev, M, N, act):
+    torch.manual_seed(M + N)
+    L = _lib.lib()
+    x = torch.randn(M, 768, device=dev) * 1.7 + 0.2
+    x[:, 5] += 9.0                                   # an outlier channel, as real residual streams have
+    gamma = torch.randn(768, device=dev) * 0.1 + 1.0
+    beta = torch.randn(768, device=dev) * 0.1
+    W = torch.randn(N, 768, device=dev) * 0.04
+    b = torch.randn(N, device=dev) * 0.1
+    xb = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+    stats = torch.empty(M, 6, 2, device=dev)
+    _lib.check(L.dvst_rowstats768(_lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), M, _lib.cur_stream()))
+    assert torch.equal(xb, x.bfloat16())
+    assert torch.allclose(stats[:, :, 0].double(), x.double().view(M, 6, 128).sum(-1), rtol=1e-5, atol=1e-3)
+    wf = (W.double() * gamma.double()[None, :]).float().bfloat16().contiguous()
+    sf = wf.double().sum(1).float().contiguous()
+    bf = (b.double() + W.double() @ beta.double()).float().contiguous()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    _lib.check(L.dvst_gemm_bf16_ln(_lib.ptr(xb), 768, _lib.ptr(wf), 768, _lib.ptr(bf), M, N, 768, _lib.ptr(stats),
+                                   _lib.ptr(sf), 1e-6, None, 0, None, 0, None, _lib.ptr(out), N, act,
+                                   _lib.cur_stream()))
+    ref = torch.nn.functional.layer_norm(x.double(), (768,), gamma.double(), beta.double(), 1e-6) @ W.double().t() + b.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    # same error budget as LayerNorm -> bf16 -> GEMM -> bf16: operand and output rounding
+    assert _rel(out.float(), ref) < 6e-3

@@ -95,6 +95,31 @@ def test_cls_only_last_block_matches_full_forward(dev, att, prec):
     assert _rel(cls_only, full) < (3e-3 if prec == "bf16" else 2e-5)
 
 
+def test_deferred_layernorm_matches_standalone_layernorm(dev):
+    """bf16 precision runs the deferred-LayerNorm path by default (residual GEMMs emit bf16(x) + row statistics, the
+    next GEMM applies the normalisation in its epilogue); forcing the stand-alone LayerNorm kernel must give the same
+    features up to bf16 rounding, for every attention type and for the get_all / CLS-only outputs."""
+    from dvst_b200 import _lib
+    L = _lib.lib()
+    for att in ("divided_space_time", "joint_space_time", "space_only"):
+        m = build(dev, 4, 2, att, "bf16")
+        x = synth_clips(41, 3, 4).to(dev)
+        try:
+            with torch.no_grad():
+                L.dvst_set_ln_fusion(0)
+                n0 = _lib.launch_count()
+                f0, a0 = m(x), m.forward_features(x, get_all=True)
+                n_plain = _lib.launch_count() - n0
+                L.dvst_set_ln_fusion(1)
+                n0 = _lib.launch_count()
+                f1, a1 = m(x), m.forward_features(x, get_all=True)
+                n_fused = _lib.launch_count() - n0
+        finally:
+            L.dvst_set_ln_fusion(1)
+        assert n_fused < n_plain                       # the LayerNorm launches are gone
+        assert _rel(f1, f0) < 1.5e-2 and _rel(a1, a0) < 1.5e-2   # two bf16 paths, each ~6e-3 from fp32
+
+
 @pytest.mark.parametrize("prec", ["bf16", "high"])
 def test_attention_map_vs_reference_golden(dev, prec):
     """forward_features(x, get_attn=True): last block's spatial attention map, against the reference's own output."""
