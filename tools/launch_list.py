@@ -1,0 +1,70 @@
+"""Aggregate an ncu launch list (CSV from `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+--clock-control none --csv --log-file X.csv python bench.py ...`) by kernel and refresh profiles/gemm_traffic.json.
+
+    python tools/launch_list.py gpurun_out/launches.csv profiles/r01_launches_bench.txt "python bench.py --steps 2 --warmup 1"
+"""
+import csv
+import json
+import os
+import re
+import sys
+
+src, dst = sys.argv[1], sys.argv[2]
+cmd = sys.argv[3] if len(sys.argv) > 3 else "python bench.py"
+rows = []
+with open(src, newline="") as f:
+    lines = [l for l in f if l.startswith('"')]
+for r in csv.DictReader(lines):
+    rows.append(r)
+per = {}
+for r in rows:
+    k = per.setdefault(r["ID"], {"name": r["Kernel Name"]})
+    v = float(r["Metric Value"].replace(",", "")) if r["Metric Value"] not in ("", "n/a") else 0.0
+    unit = r["Metric Unit"]
+    if r["Metric Name"] == "gpu__time_duration.sum":
+        k["us"] = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
+    else:
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        k["rd" if "read" in r["Metric Name"] else "wr"] = v * scale
+
+
+def short(n):
+    n = re.sub(r"\(.*", "", n)
+    n = n.replace("void ", "").replace("dvst::<unnamed>::", "").replace("<unnamed>::", "").replace("dvst::", "")
+    return n[:58]
+
+
+agg = {}
+for k in per.values():
+    a = agg.setdefault(short(k["name"]), {"n": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
+    a["n"] += 1
+    a["us"] += k.get("us", 0.0)
+    a["rd"] += k.get("rd", 0.0)
+    a["wr"] += k.get("wr", 0.0)
+tot = sum(a["us"] for a in agg.values())
+out = [f"# ncu launch list of `{cmd}` ({len(per)} launches), aggregated by kernel.",
+       "# --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; cold-cache, "
+       "serialised: compare SHARES.",
+       f"# total device time captured: {tot / 1e3:.2f} ms over {len(per)} launches",
+       f"{'kernel':60s} {'launches':>8s} {'time ms':>9s} {'share':>7s} {'avg us':>8s} {'rd MB/launch':>13s} {'wr MB/launch':>13s}"]
+for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+    out.append(f"{name:60s} {a['n']:8d} {a['us'] / 1e3:9.3f} {100 * a['us'] / tot:6.1f}% {a['us'] / a['n']:8.1f} "
+               f"{a['rd'] / a['n'] / 1e6:13.1f} {a['wr'] / a['n'] / 1e6:13.1f}")
+open(dst, "w").write("\n".join(out) + "\n")
+print("\n".join(out[:14]))
+
+big = [k for k in per.values() if "gemm_bf16_tn_kernel<2" in k["name"].replace("(int)", "")]
+if big:
+    dv = [k for k in per.values() if "dvst" in k["name"]]
+    info = {
+        "source": f"ncu launch list of `{cmd}` ({os.path.basename(dst)}): cold-cache, serialised; 2-CTA GEMM launches",
+        "gemm_launches": len(big),
+        "dram_bytes_per_launch": sum(k.get("rd", 0.0) + k.get("wr", 0.0) for k in big) / len(big),
+        "gemm_share_of_dvst_kernel_time": sum(k.get("us", 0.0) for k in big) / max(sum(k.get("us", 0.0) for k in dv), 1e-9),
+        "algorithmic_bytes_note": "per launch the operands + outputs are read / written once (qkv: 308 MB A + 3.5 MB W + "
+                                  "925 MB out; deferred-LayerNorm producers additionally read the 616 MB residual and write "
+                                  "616 MB + the 308 MB bf16 copy)",
+    }
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    json.dump(info, open(os.path.join(root, "profiles", "gemm_traffic.json"), "w"), indent=1)
+    print(info)
