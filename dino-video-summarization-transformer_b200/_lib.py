@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdvst.so")
+# DVST_LIB: load another build of the library (same-box A/B runs of two kernel versions); default = the in-tree build
+LIB_PATH = os.environ.get("DVST_LIB") or os.path.join(_HERE, "csrc", "libdvst.so")
 
 _lib = None
 

@@ -99,6 +99,52 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-ax, q, fmaxf(x, 0.0f));
 }
 
+// Packed fp32x2 arithmetic (sm_100 FFMA2): two IEEE fp32 FMAs per issued instruction.  The GELU epilogue of fc1 is
+// issue-bound next to the 256x256x768 MMA (ncu: 20 warp instructions per element, tensor pipe 62 % active), so the
+// polynomial / scaling work is done on register pairs; the MUFU ops (rcp, ex2) stay scalar.  Same operations in the same
+// order as gelu_erf(), i.e. bit-identical results.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t splat2(float v) { return pk2(v, v); }
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
+  float x0, x1;
+  unpk2(x2, x0, x1);
+  const uint64_t nax2 = x2 | 0x8000000080000000ull;  // -|x|
+  float d0, d1;
+  unpk2(fma2(splat2(-0.3275911f * 0.70710678118654752440f), nax2, splat2(1.0f)), d0, d1);
+  const uint64_t t2 = pk2(rcp_approx(d0), rcp_approx(d1));
+  uint64_t p2 = fma2(splat2(0.5f * 1.061405429f), t2, splat2(0.5f * -1.453152027f));
+  p2 = fma2(p2, t2, splat2(0.5f * 1.421413741f));
+  p2 = fma2(p2, t2, splat2(0.5f * -0.284496736f));
+  p2 = fma2(p2, t2, splat2(0.5f * 0.254829592f));
+  float a0, a1;
+  unpk2(mul2(mul2(x2, splat2(-0.72134752044448170368f)), x2), a0, a1);
+  const uint64_t e2 = pk2(ex2_approx(a0), ex2_approx(a1));
+  const uint64_t q2 = mul2(mul2(p2, t2), e2);
+  return fma2(nax2, q2, pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -324,7 +370,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col_base;
           uint32_t v[32];
           tmem_ld_32x32(trow, v);
-          float s1 = 0.f, s2 = 0.f;
+          uint64_t s1 = 0ull, s2 = 0ull;  // packed (even, odd column) partial sums
           float2* stat_row = reinterpret_cast<float2*>(p.stats_out) +
                              (static_cast<long long>(grow + lane) * (2 * p.num_n_blocks) + 2 * n_blk + (col_base >> 7));
 #pragma unroll 1
@@ -354,17 +400,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            : "r"(addr) : "memory");
               const float4 b4 = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol0) + j)
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-              w[4 * j] = (w[4 * j] + b4.x) + r4.x;
-              w[4 * j + 1] = (w[4 * j + 1] + b4.y) + r4.y;
-              w[4 * j + 2] = (w[4 * j + 2] + b4.z) + r4.z;
-              w[4 * j + 3] = (w[4 * j + 3] + b4.w) + r4.w;
+              const uint64_t wa = add2(add2(pk2(w[4 * j], w[4 * j + 1]), pk2(b4.x, b4.y)), pk2(r4.x, r4.y));
+              const uint64_t wb = add2(add2(pk2(w[4 * j + 2], w[4 * j + 3]), pk2(b4.z, b4.w)), pk2(r4.z, r4.w));
+              s1 = add2(add2(s1, wa), wb);
+              s2 = fma2(wb, wb, fma2(wa, wa, s2));
+              unpk2(wa, w[4 * j], w[4 * j + 1]);
+              unpk2(wb, w[4 * j + 2], w[4 * j + 3]);
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(w[4 * j]), "f"(w[4 * j + 1]),
                            "f"(w[4 * j + 2]), "f"(w[4 * j + 3]) : "memory");
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              s1 += w[j];
-              s2 = fmaf(w[j], w[j], s2);
             }
             const uint32_t bbox = bst + (g & 1) * (STG_BUF_BYTES / 2) + brow_off;
 #pragma unroll
@@ -390,9 +433,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             __syncwarp();
             if ((c & 3) == 3) {  // 128 columns done: one partial
-              if (grow + lane < p.M) stat_row[c >> 2] = make_float2(s1, s2);
-              s1 = 0.f;
-              s2 = 0.f;
+              float s1a, s1b, s2a, s2b;
+              unpk2(s1, s1a, s1b);
+              unpk2(s2, s2a, s2b);
+              if (grow + lane < p.M) stat_row[c >> 2] = make_float2(s1a + s1b, s2a + s2b);
+              s1 = 0ull;
+              s2 = 0ull;
             }
           }
           if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
@@ -477,34 +523,36 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 else mbar_arrive_cluster(tempty_bar + 8 * a, 0);
               }
             }
-            float f[32];
+            uint64_t f2[16];  // register pairs (columns 2j, 2j + 1)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(cur[j]);
+            for (int j = 0; j < 16; ++j) f2[j] = pk2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]));
+            const uint64_t rstd2 = splat2(ln_rstd), nmr2 = splat2(ln_nmr);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {  // branch-free: a null bias adds zeros
               const float4 b4 = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + hh * 32) + j4)
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
               if constexpr (kLN == 1) {
                 const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + gcol0 + hh * 32) + j4);
-                f[4 * j4] = fmaf(ln_rstd, f[4 * j4], fmaf(ln_nmr, s4.x, b4.x));
-                f[4 * j4 + 1] = fmaf(ln_rstd, f[4 * j4 + 1], fmaf(ln_nmr, s4.y, b4.y));
-                f[4 * j4 + 2] = fmaf(ln_rstd, f[4 * j4 + 2], fmaf(ln_nmr, s4.z, b4.z));
-                f[4 * j4 + 3] = fmaf(ln_rstd, f[4 * j4 + 3], fmaf(ln_nmr, s4.w, b4.w));
+                f2[2 * j4] = fma2(rstd2, f2[2 * j4], fma2(nmr2, pk2(s4.x, s4.y), pk2(b4.x, b4.y)));
+                f2[2 * j4 + 1] = fma2(rstd2, f2[2 * j4 + 1], fma2(nmr2, pk2(s4.z, s4.w), pk2(b4.z, b4.w)));
               } else {
-                f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
+                f2[2 * j4] = add2(f2[2 * j4], pk2(b4.x, b4.y));
+                f2[2 * j4 + 1] = add2(f2[2 * j4 + 1], pk2(b4.z, b4.w));
               }
             }
             if constexpr (kAct == 1) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              for (int j = 0; j < 16; ++j) f2[j] = gelu_erf2(f2[j]);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const uint32_t hw = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+              float fa, fb;
+              unpk2(f2[j], fa, fb);
+              const uint32_t hw = pack_bf16x2(fa, fb);
               hi[hh * 16 + j] = hw;
               if constexpr (kOut == 2) {
                 const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hw);
-                lo[hh * 16 + j] = pack_bf16x2(f[2 * j] - __low2float(hb), f[2 * j + 1] - __high2float(hb));
+                lo[hh * 16 + j] = pack_bf16x2(fa - __low2float(hb), fb - __high2float(hb));
               }
             }
           }

@@ -86,6 +86,20 @@ def export_loss(loss_list, video_path, file_path):
             json.dump(video_dict, file)
 
 
+def export_losses(losses_by_video, file_path):
+    """export_loss for several videos with ONE read-modify-write of the JSON (the reference rewrites the whole file
+    once per video, dino_similarity.py:97-117 - quadratic in the number of videos).  `losses_by_video` is an ordered
+    mapping video_path -> loss list; the resulting file is identical to calling export_loss for each entry in order."""
+    video_dict = {os.path.splitext(os.path.basename(path))[0]: loss for path, loss in losses_by_video.items()}
+    merged = {}
+    if os.path.exists(file_path):
+        with open(file_path, 'r') as file:
+            merged = json.load(file).copy()
+    merged.update(video_dict)
+    with open(file_path, 'w') as file:
+        json.dump(merged, file)
+
+
 def preprocess_frames(video_uint8, sampling_rate=4, mean=(0.45, 0.45, 0.45), std=(0.225, 0.225, 0.225), crop_size=224):
     """Loader front half (datasets_custom/dino_loss_loader.py:80-92): raw decoded video uint8 [n,H,W,3] -> every
     `sampling_rate`-th frame, /255, mean/std normalised (data_utils.py:308-325), T H W C -> T C H W, centre crop
@@ -293,7 +307,7 @@ def dino_similarity(cfg, local_clip_size, global_clip_size, sampling_rate, file_
     `model` is None it is built exactly like the reference does (get_vit_base_patch16_224 + "backbone."-stripped
     checkpoint from cfg.pretrained_weights).  `videos_per_batch` videos are scored per backbone pass
     (score_videos_device: same losses as one at a time) and their F-float loss vectors come back in one D2H copy each;
-    the JSON is still merged video by video in dataset order (export_loss)."""
+    the JSON is merged once per batch (export_losses: same file content as the reference's per-video export_loss)."""
     from .models import get_vit_base_patch16_224
     if dataset is None:
         raise ValueError("pass `dataset`: an iterable of (frames, file_name); video decoding is not part of this path")
@@ -312,10 +326,11 @@ def dino_similarity(cfg, local_clip_size, global_clip_size, sampling_rate, file_
         with torch.no_grad():
             losses = score_videos_device(model, [f for f, _ in batch], dino_loss, local_clip_size, global_clip_size,
                                          scorer=scorer)
+        out = {}
         for (_, file_name), loss in zip(batch, losses):
-            loss = loss.tolist()
-            export_loss(loss, file_name, file_path)
-            results[os.path.splitext(os.path.basename(file_name))[0]] = loss
+            out[file_name] = loss.tolist()
+            results[os.path.splitext(os.path.basename(file_name))[0]] = out[file_name]
+        export_losses(out, file_path)
 
     batch = []
     for frames, file_name in dataset:

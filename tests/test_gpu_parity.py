@@ -204,6 +204,28 @@ def test_driver_golden_and_invariants(dev):
         assert _relmax(got, ref) < LOSS_TOL  # reference-exact mode R through the reference's own driver loop
 
 
+def test_driver_function_writes_reference_json(dev, tmp_path):
+    """dvst_b200.dino_similarity.dino_similarity (the drop-in driver, batched) against the JSON the reference's own
+    driver wrote for the same two videos (tests/golden/driver_loss.json): same keys, lengths, losses within 1e-3."""
+    from dvst_b200.dino_similarity import dino_similarity
+    D = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "driver_loss.json")))
+    m = build(dev, D["seed_w"], 12, prec="high")
+    data = []
+    for name, meta in D["videos"].items():
+        g = torch.Generator().manual_seed(meta["seed"])
+        raw = torch.randint(0, 256, (meta["n_unsampled"], 224, 224, 3), generator=g, dtype=torch.uint8)
+        data.append((preprocess_frames(raw.to(dev), 4), f"/some/dir/{name}.avi"))
+    out = str(tmp_path / "loss.json")
+    for vpb in (1, 8):
+        if os.path.exists(out):
+            os.remove(out)
+        res = dino_similarity(None, 3, 30, 4, out, dataset=data, model=m, videos_per_batch=vpb)
+        written = json.load(open(out))
+        assert list(written.keys()) == list(D["loss"].keys()) and written == res
+        for name, ref in D["loss"].items():
+            assert len(written[name]) == len(ref) and _relmax(written[name], ref) < LOSS_TOL
+
+
 def test_dummy_video_path(dev):
     m = build(dev, 1, 2)
     with torch.no_grad():
@@ -225,17 +247,17 @@ def test_scoring_vs_oracle_and_selected_indices(dev):
     head.load_state_dict(hsd, strict=True)
     head = head.to(dev).eval()
     same, total = 0, 0
-    for seed, F in [(1, 5), (2, 9), (3, 12), (4, 7)]:
+    for seed, F in [(1, 5), (2, 9), (3, 12), (4, 7), (5, 3), (6, 16), (7, 6), (8, 11), (9, 14), (10, 8)]:
         frames = synth_video(seed, F, smooth=0.5)
         ref = O.score_video(sd, frames, local_size=3, global_size=6, teacher_temp=0.04, student_temp=0.1, head=hsd)
         with torch.no_grad():
             got = score_video(m, frames.to(dev), local_clip_size=3, global_clip_size=6,
                               scorer=HeadScorer(head, 0.04, 0.1))
         assert len(got) == F and _relmax(got, ref) < LOSS_TOL
-        for N in (2, 4):
+        for N in (2, 4, 8):
             total += 1
             same += select_frames_adaptive(got, 4 * F, 4, N) == select_frames_adaptive(ref, 4 * F, 4, N)
-    assert same == total
+    assert total == 30 and same == total
 
 
 def test_batched_videos_equal_one_at_a_time(dev):

@@ -10,7 +10,7 @@ import torch
 
 import dvst_b200  # noqa: F401
 from dvst_b200 import _lib
-from dvst_b200.dino_similarity import DINOLoss, export_loss, preprocess_frames, window_starts
+from dvst_b200.dino_similarity import DINOLoss, export_loss, export_losses, preprocess_frames, window_starts
 from dvst_b200.frame_selection import select_frames_adaptive, select_frames_uniform
 from dvst_b200.models import TimeSformer, VisionTransformer, get_vit_base_patch16_224, vit_base_patch16_224
 from dvst_b200.parallel import shard_videos, video_cost
@@ -98,6 +98,21 @@ def test_export_loss_format(tmp_path):
     export_loss([3.0], "/x/def.mp4", p)
     export_loss([9.0], "abc_1_2.avi", p)  # read-modify-write: later result replaces the earlier one
     assert open(p).read() == '{"abc_1_2": [9.0], "def": [3.0]}'
+
+
+def test_export_losses_equals_sequential_export_loss(tmp_path):
+    """One read-modify-write for a batch of videos leaves the same file as the reference's per-video export_loss."""
+    a, b = str(tmp_path / "a.json"), str(tmp_path / "b.json")
+    items = [("/d/v1.avi", [1.0, 2.0]), ("/d/v2.mp4", [0.5]), ("/e/v1.avi", [7.0]), ("v3.avi", [3.25, 4.5, 1e-3])]
+    export_loss([8.0], "old.avi", a)
+    export_loss([8.0], "old.avi", b)
+    for path, loss in items[:2]:
+        export_loss(loss, path, a)
+    for path, loss in items[2:]:
+        export_loss(loss, path, a)
+    export_losses(dict(items[:2]), b)
+    export_losses(dict(items[2:]), b)
+    assert open(a).read() == open(b).read()
 
 
 def test_preprocess_frames():
