@@ -67,6 +67,9 @@ SIGNATURES = {
     "dvst_knn_topk": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "dvst_knn_vote": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p,
                               c_void_p, c_void_p]),
+    "dvst_attention_scratch_bytes": (c_ll, [c_int, c_int, c_int]),
+    "dvst_attention_ws": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p,
+                                  c_ll, c_void_p]),
     "dvst_attention": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p]),
 }
 

@@ -151,6 +151,16 @@ int dvst_attention(const void* qkv, long long ld, void* out, long long ldo, floa
   return launch_attention(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, 0, static_cast<cudaStream_t>(stream));
 }
 
+long long dvst_attention_scratch_bytes(int B, int T, int N) {
+  return (B > 0 && T > 0 && N > 0) ? spatial_attention_scratch_bytes(B, T, N) : 0;
+}
+
+int dvst_attention_ws(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                      int N, long long cls_base, void* scratch, long long scratch_bytes, void* stream) {
+  return launch_attention(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, 0, static_cast<cudaStream_t>(stream),
+                          scratch, scratch_bytes);
+}
+
 int dvst_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int n_videos,
                        int pre_sampling_rate, int num_frames, int* indices, void* stream) {
   if (loss == nullptr || n_loss == nullptr || n_unsampled == nullptr || indices == nullptr)

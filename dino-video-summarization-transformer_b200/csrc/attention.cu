@@ -698,7 +698,7 @@ int launch_cls_attention(const void* qkv, long long ld, void* out, long long ldo
 }
 
 int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
-                     int N, long long cls_base, int split, cudaStream_t st) {
+                     int N, long long cls_base, int split, cudaStream_t st, void* scratch, long long scratch_bytes) {
   AttnParams p;
   p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
   p.ld = ld;
@@ -733,7 +733,7 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
   const size_t per = static_cast<size_t>(S_pad) * 128;
   int rc = 0;
   if (!split && (mode == 1 || mode == 3)) {
-    rc = launch_spatial_attention_sm100(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, st);
+    rc = launch_spatial_attention_sm100(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, st, scratch, scratch_bytes);
     if (rc == 0) { count_launch(); return 0; }
     if (rc != 1) return rc;
     rc = 0;

@@ -13,6 +13,13 @@
 //                 i.e. the K dimension, so no transpose copy), M = 128, N = 64, K = NPAD               -> TMEM fp32
 //   epilogue    : tcgen05.ld O, scale by 1 / row sum, bf16, swizzled staging tile, 3-D TMA store back to the token rows
 //
+// One-pass softmax (kOnePass, used when the caller provides scratch): softmax is invariant to the reference point, and any
+// reference within ~44 nats of the row maximum keeps every exp2 and the fp32 / bf16 sums in range, so the reference is
+// the maximum of the FIRST 32 keys only (one TMEM round trip instead of a full pass over S).  A row whose exponentials
+// still grow past 2^64 (its maximum lies > 44 nats above those 32 keys) is appended to a fix-up list, and
+// attention_fixup_kernel recomputes exactly those rows in fp32 from the packed qkv afterwards - results stay exact for
+// every input, the common case pays nothing.
+//
 // Warp roles (384 threads): warp 0 TMA producer + CLS-row copy, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
 // softmax / epilogue of row tile A (rows 0-127), warps 8-11 of row tile B (rows 128-255).  TMEM: 2 x 256 columns; per
 // tile S occupies [0, NPAD), P overwrites [0, NPAD/2), O lands in [128, 192) once S has been consumed.
@@ -41,6 +48,8 @@ struct SpParams {
   int n_prob, heads;
   long long cls_base;
   int rows_a, rows_b;   // patch rows of tile A / tile B (what the TMA stores cover)
+  int* fix_count;       // one-pass softmax: number of rows to recompute ...
+  int2* fix_list;       // ... and their (problem, row) pairs (capacity n_prob * S)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -51,6 +60,30 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// sm_100 packed / 3-input fp32 forms: half the issue slots for the softmax's scaling, row-sum and row-max work
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -97,6 +130,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src_
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+template <bool kOnePass>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOutA,
                                const __grid_constant__ CUtensorMap tmOutB, const SpParams p) {
@@ -265,21 +299,22 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
         const int b = seq / p.T, t = seq - b * p.T;
         mbar_wait(sfull_bar + 8 * tile, tp);
         tc_fence_after();
-        // ---- pass 1: row max ----
+        // ---- pass 1: row max (one-pass softmax: of the first 32 keys only) ----
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         {
           uint32_t v[32], v2[32];
           tmem_ld_32x32(treg, v);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < (kOnePass ? 1 : 8); ++c) {
             if (c < nch) {
               uint32_t (&cur)[32] = (c & 1) ? v2 : v;
               uint32_t (&nxt)[32] = (c & 1) ? v : v2;
               tmem_ld_wait();
-              if (c + 1 < nch) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
+              if (!kOnePass && c + 1 < nch) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
               if (c * 32 + 32 <= S) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(cur[j]));
+                for (int j = 0; j < 16; ++j)
+                  mx4[j & 3] = max3(mx4[j & 3], __uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]));
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -291,7 +326,8 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
         // ---- pass 2: p = exp2((s - max) * scale), row sum, P -> TMEM (bf16 pairs over the consumed S columns) ----
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const float moff = mx * scale_log2;
-        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint64_t sum2[2] = {0ull, 0ull};
+        const uint64_t scale2 = pk2(scale_log2, scale_log2), nmoff2 = pk2(-moff, -moff);
         {
           uint32_t v[32], v2[32];
           tmem_ld_32x32(treg, v);
@@ -303,18 +339,22 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
               tmem_ld_wait();
               if (c + 1 < nch) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
               float e[32];
-              if (c * 32 + 32 <= S) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(cur[j]), scale_log2, -moff));
-              } else {
+              for (int j = 0; j < 16; ++j) {
+                float a0, a1;
+                unpk2(fma2(pk2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), scale2, nmoff2), a0, a1);
+                e[2 * j] = ex2_approx(a0);
+                e[2 * j + 1] = ex2_approx(a1);
+              }
+              if (c * 32 + 32 > S) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  e[j] = c * 32 + j < S ? ex2_approx(fmaf(__uint_as_float(cur[j]), scale_log2, -moff)) : 0.f;
+                  if (c * 32 + j >= S) e[j] = 0.f;
               }
               uint32_t pk[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                sum4[j & 3] += e[2 * j] + e[2 * j + 1];
+                sum2[j & 1] = add2(sum2[j & 1], pk2(e[2 * j], e[2 * j + 1]));
                 pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
               }
               tmem_st_32x16(treg + c * 16, pk);
@@ -335,7 +375,13 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(oempty_bar + 8 * tile);
-        const float inv = 1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+        float sa, sb;
+        unpk2(add2(sum2[0], sum2[1]), sa, sb);
+        const float inv = 1.0f / (sa + sb);
+        if constexpr (kOnePass) {
+          // exponentials past 2^64 (or NaN): this row is recomputed exactly by attention_fixup_kernel
+          if (row < S && !(sa + sb < 1.8e19f)) p.fix_list[atomicAdd(p.fix_count, 1)] = make_int2(prob, row);
+        }
         // the previous problem's TMA store must have finished reading the staging tile
         if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         named_bar_sync(1 + tile, n_act * 32);
@@ -398,14 +444,101 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
   }
 }
 
+// Exact fp32 recomputation of the rows the one-pass softmax could not normalise: one warp per (problem, row).
+__global__ void __launch_bounds__(128) attention_fixup_kernel(const SpParams p) {
+  const int n_fix = *p.fix_count;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n_fix; i += n_warps) {
+    const int2 e = p.fix_list[i];
+    const int prob = e.x, row = e.y;
+    const int seq = prob / p.heads, head = prob - seq * p.heads;
+    const int b = seq / p.T, t = seq - b * p.T;
+    const long long cls_row = p.cls_base + (p.mode == 1 ? b : seq);
+    auto token_row = [&](int j) { return j < p.N ? (static_cast<long long>(b) * p.N + j) * p.T + t : cls_row; };
+    const __nv_bfloat16* qp = p.qkv + token_row(row) * p.ld + head * HD;
+    float q[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] = __bfloat162float(qp[d]);
+    // scores of this lane's keys (j = lane, lane + 32, ...): S <= 256 -> at most 8 per lane
+    float sc[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = lane + 32 * u;
+      sc[u] = -INFINITY;
+      if (j < p.S) {
+        const __nv_bfloat16* kp = p.qkv + token_row(j) * p.ld + DMODEL + head * HD;
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc = fmaf(q[d], __bfloat162float(kp[d]), acc);
+        sc[u] = acc * 0.125f;
+        mx = fmaxf(mx, sc[u]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    float sum = 0.f;
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = lane + 32 * u;
+      if (j < p.S) {
+        const float w = expf(sc[u] - mx);
+        sum += w;
+        const __nv_bfloat16* vp = p.qkv + token_row(j) * p.ld + 2 * DMODEL + head * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = fmaf(w, __bfloat162float(vp[d]), acc[d]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    const float inv = 1.0f / sum;
+    // reduce the 64 output dims over the warp; lane d (and d + 32) keeps dims d, d + 32
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      float v = acc[d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if ((d & 31) == lane) { if (d < 32) o0 = v; else o1 = v; }
+    }
+    o0 *= inv;
+    o1 *= inv;
+    if (row < p.N) {
+      __nv_bfloat16* dst = p.out + token_row(row) * p.ldo + head * HD;
+      dst[lane] = __float2bfloat16(o0);
+      dst[lane + 32] = __float2bfloat16(o1);
+    } else if (p.mode == 1) {
+      float* dst = p.cls_out + static_cast<long long>(seq) * DMODEL + head * HD;
+      dst[lane] = o0;
+      dst[lane + 32] = o1;
+    } else {
+      __nv_bfloat16* dst = p.out + (p.cls_base + seq) * p.ldo + head * HD;
+      dst[lane] = __float2bfloat16(o0);
+      dst[lane + 32] = __float2bfloat16(o1);
+    }
+  }
+}
+
 }  // namespace
 
-static int g_attention_impl = 1;  // 1 = tcgen05 kernel where it applies, 0 = mma.sync kernels only
-void set_attention_impl(int impl) { g_attention_impl = impl != 0 ? 1 : 0; }
+// 1 = tcgen05 kernel where it applies (one-pass softmax when scratch is given), 2 = tcgen05 with the two-pass softmax,
+// 0 = mma.sync kernels only
+static int g_attention_impl = 1;
+void set_attention_impl(int impl) { g_attention_impl = impl == 0 ? 0 : (impl == 2 ? 2 : 1); }
 
 // Returns 1 if the shape is not handled here (the caller falls back to the mma.sync kernels), 0 on success, < 0 error.
+long long spatial_attention_scratch_bytes(int B, int T, int N) {
+  return 256 + static_cast<long long>(B) * T * 12 * (N + 1) * static_cast<long long>(sizeof(int2));
+}
+
 int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode,
-                                   int B, int T, int N, long long cls_base, cudaStream_t st) {
+                                   int B, int T, int N, long long cls_base, cudaStream_t st, void* scratch,
+                                   long long scratch_bytes) {
   if (!g_attention_impl) return 1;
   const int S = N + 1;
   if ((mode != 1 && mode != 3) || S > 256 || N < 1) return 1;
@@ -430,11 +563,19 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
   const size_t smem = 1024 + 2 * (n_tiles * TILE_BYTES + 2 * kv_bytes) + n_tiles * TILE_BYTES + 128;
   static size_t cur = 0;
   if (smem > cur) {
-    cudaError_t e = cudaFuncSetAttribute(spatial_attention_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(spatial_attention_sm100_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(spatial_attention_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
     if (e != cudaSuccess) return set_error("attention(sm100) attr: %s", cudaGetErrorString(e));
     cur = smem;
   }
+  // one-pass softmax needs the fix-up list: counter at scratch[0], entries from scratch + 256
+  const bool one_pass = g_attention_impl == 1 && scratch != nullptr && scratch_bytes >= spatial_attention_scratch_bytes(B, T, N) &&
+                        (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
+  p.fix_count = static_cast<int*>(scratch);
+  p.fix_list = reinterpret_cast<int2*>(static_cast<uint8_t*>(scratch) + 256);
   const uint64_t BN = static_cast<uint64_t>(B) * N;
   CUtensorMap tmIn, tmOutA, tmOutB;
   if (int rc = make_tmap_bf16_3d(&tmIn, qkv, 3 * DMODEL, T, BN, ld * 2, static_cast<uint64_t>(T) * ld * 2, HD, 1, N))
@@ -446,7 +587,15 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
                                  p.rows_b > 0 ? p.rows_b : 1))
     return rc;
   const int grid = p.n_prob < num_sms() ? p.n_prob : num_sms();
-  spatial_attention_sm100_kernel<<<grid, NUM_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p);
+  if (one_pass) {
+    cudaError_t e = cudaMemsetAsync(p.fix_count, 0, sizeof(int), st);
+    if (e != cudaSuccess) return set_error("attention(sm100) memset: %s", cudaGetErrorString(e));
+    spatial_attention_sm100_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p);
+    attention_fixup_kernel<<<grid < 64 ? grid : 64, 128, 0, st>>>(p);
+    count_launch();
+  } else {
+    spatial_attention_sm100_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : set_error("attention(sm100) launch: %s", cudaGetErrorString(e));
 }

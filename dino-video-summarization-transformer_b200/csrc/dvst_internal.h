@@ -74,8 +74,12 @@ int launch_pair_loss(const float* s, long long lds, const float* t, long long ld
 int launch_embed_table(const float* pos, int P, const float* time_embed, int T0, float* out, int gh, int gw, int T,
                        cudaStream_t st);
 // mode: 0 temporal, 1 spatial (shared CLS per clip), 2 joint, 3 space-only (one CLS row per (b, t))
+// scratch (optional, modes 1 / 3): >= spatial_attention_scratch_bytes(B, T, N) bytes enables the one-pass softmax of the
+// tcgen05 kernel (fix-up list of rows to recompute exactly)
 int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
-                     int N, long long cls_base, int split, cudaStream_t st);
+                     int N, long long cls_base, int split, cudaStream_t st, void* scratch = nullptr,
+                     long long scratch_bytes = 0);
+long long spatial_attention_scratch_bytes(int B, int T, int N);
 
 // Same modes 1..3, but only the CLS query of every sequence attends (last block when only CLS features are returned):
 // mode 1 writes cls_out [B*T, 768] fp32, modes 2 / 3 write the CLS rows of `out`.
@@ -87,8 +91,9 @@ int launch_attention_probs(const void* qkv, long long ld, float* probs, int B, i
 // tcgen05 / TMEM kernel for modes 1 and 3 (bf16): returns 0 when it ran, 1 when the shape is not covered (callers then
 // use the mma.sync kernels), anything else is an error code.
 int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode,
-                                   int B, int T, int N, long long cls_base, cudaStream_t st);
-void set_attention_impl(int impl);  // 1 (default) = tcgen05 where it applies, 0 = mma.sync kernels only; test hook
+                                   int B, int T, int N, long long cls_base, cudaStream_t st, void* scratch = nullptr,
+                                   long long scratch_bytes = 0);
+void set_attention_impl(int impl);  // 1 (default) tcgen05 (+ one-pass softmax with scratch), 2 tcgen05 two-pass, 0 mma.sync
 
 int launch_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int V, int rate,
                          int N, int* out, cudaStream_t st);

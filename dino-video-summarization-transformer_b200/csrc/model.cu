@@ -62,6 +62,8 @@ struct Workspace {
   float* tmp;  // [rows, 768] fp32 scratch for space_only's frame mean
   void* xb;     // bf16 [M, 768] copy of x (deferred LayerNorm: the A operand of the consuming GEMM)
   float* stats; // fp32 [M, 6, 2] per-128-column (sum, sumsq) of every row of x
+  void* attn_scratch;  // fix-up list of the one-pass spatial softmax
+  size_t attn_scratch_bytes;
   size_t total;
 };
 
@@ -89,6 +91,9 @@ static Workspace carve(const Model& m, void* base, long long B, int T, int gh, i
   const bool fl = m.fused_ln && m.cfg.precision == DVST_PRECISION_BF16;
   w.xb = take(fl ? static_cast<size_t>(M) * D * 2 : 1024);
   w.stats = static_cast<float*>(take(fl ? static_cast<size_t>(M) * 12 * 4 : 1024));
+  w.attn_scratch_bytes = m.cfg.attention_type == DVST_ATTN_JOINT
+                             ? 0 : static_cast<size_t>(spatial_attention_scratch_bytes(static_cast<int>(B), T, static_cast<int>(N)));
+  w.attn_scratch = take(w.attn_scratch_bytes ? w.attn_scratch_bytes : 1024);
   w.total = off;
   return w;
 }
@@ -383,7 +388,8 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
     }
     if (fl) DVST_TRY(gemm_ln(b.qkv_wf, b.qkv_sf, b.qkv_bf, 0, M, 3 * D, w.qkv, ldq, 0));
     else DVST_TRY(gemm(w.a, lda, b.qkv_w, b.qkv_b, M, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
-    DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, w.cls_acc, mode, B, T, static_cast<int>(N), Mt, split, st));
+    DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, w.cls_acc, mode, B, T, static_cast<int>(N), Mt, split, st,
+                              w.attn_scratch_bytes ? w.attn_scratch : nullptr, static_cast<long long>(w.attn_scratch_bytes)));
     if (att == DVST_ATTN_DIVIDED)
       DVST_TRY(launch_cls_mean(w.cls_acc, static_cast<__nv_bfloat16*>(w.a) + Mt * lda, lda, split, D, B, T, nullptr, st));
     if (fl) {

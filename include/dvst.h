@@ -47,7 +47,8 @@ int dvst_abi_version(void);
 void dvst_set_gemm_cta_group(int cg);
 
 /* Tuning / test hook: 1 (default) runs spatial / space-only attention (modes 1 and 3, up to 256 tokens, bf16) on the
- * tcgen05 + TMEM kernel; 0 forces the mma.sync kernels for every mode. */
+ * tcgen05 + TMEM kernel (one-pass softmax where scratch is available); 2 the same kernel with the two-pass softmax;
+ * 0 forces the mma.sync kernels for every mode. */
 void dvst_set_attention_impl(int impl);
 
 /* Tuning / test hook: 1 (default) lets bf16-precision models whose folded tensors are registered run the deferred
@@ -168,6 +169,13 @@ int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const f
  *   3 space-only; cls_base = index of the first CLS row; out bf16 [*, ldo]. */
 int dvst_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                    int N, long long cls_base, void* stream);
+
+/* Same with scratch (>= dvst_attention_scratch_bytes(B, T, N) bytes, 16-byte aligned): modes 1 / 3 then run the tcgen05
+ * kernel's one-pass softmax (reference point = maximum of the first 32 keys; rows it cannot normalise are recomputed
+ * exactly in fp32 by a fix-up kernel, so results are exact for every input). */
+long long dvst_attention_scratch_bytes(int B, int T, int N);
+int dvst_attention_ws(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                      int N, long long cls_base, void* scratch, long long scratch_bytes, void* stream);
 
 /* Adaptive frame selection for a batch of videos (datasets_custom/frame_selection_loader.py:115-172) on the device, in
  * the reference's fp64 arithmetic (numpy pairwise sum, sequential cumsum, first-minimum argmin): identical index lists.

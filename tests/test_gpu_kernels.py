@@ -343,3 +343,61 @@ def test_deferred_layernorm_consumer(dev, M, N, act):
         ref = torch.nn.functional.gelu(ref)
     # same error budget as LayerNorm -> bf16 -> GEMM -> bf16: operand and output rounding
     assert _rel(out.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("mode,B,T,N,adversarial", [(1, 2, 3, 196, False), (3, 2, 2, 196, False), (1, 1, 2, 36, False),
+                                                     (1, 2, 3, 196, True), (3, 1, 2, 196, True), (1, 1, 2, 36, True)])
+def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
+    """tcgen05 spatial attention with scratch: softmax referenced to the maximum of the first 32 keys.  Ordinary inputs
+    need no fix-up; adversarial ones (row maxima hundreds of nats above those 32 keys: exp2 overflows) are recomputed
+    exactly by the fix-up kernel - both must match the fp32 reference."""
+    torch.manual_seed(7 + mode + N)
+    L = _lib.lib()
+    Mt = B * N * T
+    ncls = B * T if mode == 3 else B
+    qkv = (torch.randn(Mt + ncls, 2304, device=dev) * 1.5).bfloat16()
+    if adversarial:
+        # keys whose position inside the frame is >= 40 (and the CLS keys) point along u with a large norm; every third
+        # query does too -> scores ~ +-2000 / 8 far above anything among the first 32 keys
+        u = torch.nn.functional.normalize(torch.randn(64, device=dev), dim=0)
+        rows = torch.arange(Mt, device=dev).reshape(B, N, T)
+        far_keys = rows[:, min(40, N - 1):, :].reshape(-1)
+        for h in range(12):
+            qkv[far_keys, 768 + h * 64: 768 + (h + 1) * 64] = (45.0 * u).bfloat16()
+            qkv[Mt:, 768 + h * 64: 768 + (h + 1) * 64] = (-45.0 * u).bfloat16()
+            qkv[0::3, h * 64: (h + 1) * 64] = (45.0 * u).bfloat16()
+            qkv[1::7, h * 64: (h + 1) * 64] = (-45.0 * u).bfloat16()
+    nb = L.dvst_attention_scratch_bytes(B, T, N)
+    scratch = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    out = torch.zeros(Mt + ncls, 768, device=dev, dtype=torch.bfloat16)
+    cls_out = torch.zeros(B, T, 768, device=dev)
+    _lib.check(L.dvst_attention_ws(_lib.ptr(qkv), 2304, _lib.ptr(out), 768, _lib.ptr(cls_out), mode, B, T, N, Mt,
+                                   _lib.ptr(scratch), nb, _lib.cur_stream()))
+    n_fix = int(scratch[:4].view(torch.int32)[0])
+    assert (n_fix > 0) == adversarial
+    q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
+    refo = torch.zeros(Mt + ncls, 768, device=dev)
+    refc = torch.zeros(B, T, 768, device=dev)
+    rows = torch.arange(Mt, device=dev).reshape(B, N, T)
+    for bb in range(B):
+        for t in range(T):
+            c = Mt + (bb * T + t if mode == 3 else bb)
+            r = torch.cat([torch.tensor([c], device=dev), rows[bb, :, t]])
+            o = _attn_ref(q[r], k[r], v[r])
+            refo[r[1:]] = o[1:]
+            if mode == 1:
+                refc[bb, t] = o[0]
+            else:
+                refo[c] = o[0]
+    assert torch.isfinite(out.float()).all() and torch.isfinite(cls_out).all()
+    assert _rel(out[:Mt].float(), refo[:Mt]) < 5e-3
+    if mode == 1:
+        assert _rel(cls_out, refc) < 5e-3
+    else:
+        assert _rel(out[Mt:].float(), refo[Mt:]) < 5e-3
+    # the two-pass kernel (no scratch) agrees to bf16 rounding of P
+    out2 = torch.zeros_like(out)
+    cls2 = torch.zeros_like(cls_out)
+    _lib.check(L.dvst_attention(_lib.ptr(qkv), 2304, _lib.ptr(out2), 768, _lib.ptr(cls2), mode, B, T, N, Mt,
+                                _lib.cur_stream()))
+    assert _rel(out.float(), out2.float()) < 5e-3
