@@ -102,7 +102,7 @@ def launch_count():
     return int(lib().dvst_launch_count())
 
 
-PROF_KINDS = ("gemm", "attention", "layernorm", "elementwise", "head_loss")
+PROF_KINDS = ("gemm", "attention", "layernorm", "elementwise", "head_loss", "gemm_hbm")
 
 
 def profile_enable(on):

@@ -14,8 +14,10 @@ void count_launch();
 int num_sms();
 
 // Optional live per-kernel timing (CUDA events on the launching stream), used by bench.py for the roofline figures.
+// PROF_GEMM_HBM: short-K (K <= 1024) deferred-LayerNorm producer GEMMs - bounded by their residual / output streams (work is
+// counted in bytes), unlike every other GEMM launch (tensor bound, work in FLOPs).
 enum ProfKind { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ELEMENTWISE = 3, PROF_HEAD_LOSS = 4,
-                PROF_NKINDS = 5 };
+                PROF_GEMM_HBM = 5, PROF_NKINDS = 6 };
 struct ProfScope {
   int idx;
   cudaStream_t st;

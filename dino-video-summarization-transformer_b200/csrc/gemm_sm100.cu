@@ -690,7 +690,10 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ProfScope prof(PROF_GEMM, 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
+  const bool hbm_bound = kOut == 3 && g.K <= 1024;
+  const double hbm_bytes = static_cast<double>(g.M) * (2.0 * g.K + 10.0 * g.N) + 2.0 * g.N * g.K;  // A, x in / out, xb, W
+  ProfScope prof(hbm_bound ? PROF_GEMM_HBM : PROF_GEMM,
+                 hbm_bound ? hbm_bytes : 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG, kOut, kAct, kLN>, tmA, tmB, tmO, tmXb, p);
   if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
   count_launch();

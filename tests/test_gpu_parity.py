@@ -324,3 +324,29 @@ def test_full_size_video_invariants(dev):
             assert torch.equal(dl.pair_losses(s, t).cpu()[0], loss[i])
     assert loss.shape == (68,) and torch.isfinite(loss).all()
     assert loss[0] == loss[1] and loss[-1] == loss[-2]
+
+
+def test_full_size_long_clip_and_knn_view_shapes(dev):
+    """Config 5 (32 frames, T*N = 6 272 tokens per clip, divided and joint attention) and config 4 (8-frame 224^2 global +
+    4-frame 96^2 local views grouped by MultiCropWrapper) at full model depth: finite, batch-independent features, and
+    the joint kernel (K/V streaming) agrees with itself across batch compositions bit-exactly."""
+    from dvst_b200.utils import MultiCropWrapper
+    m = build(dev, 0, 12, T0=8)
+    x = synth_clips(90, 3, 32).to(dev)
+    with torch.no_grad():
+        f = m(x)
+        f1 = m(x[1:2])
+    assert tuple(f.shape) == (3, 768) and torch.isfinite(f).all() and torch.equal(f[1:2], f1)
+    mj = build(dev, 0, 2, att="joint_space_time", T0=8)
+    with torch.no_grad():
+        fj = mj(x[:2])
+        fj1 = mj(x[1:2])
+    assert torch.isfinite(fj).all() and torch.equal(fj[1:2], fj1)
+    # config 4: two resolutions / frame counts through the wrapper = the same features as separate forwards
+    g = synth_clips(91, 4, 8).to(dev)
+    l = synth_clips(92, 4, 4, 96, 96).to(dev)
+    w = MultiCropWrapper(m, torch.nn.Identity())
+    with torch.no_grad():
+        out = w([g, l])
+        fg, fl_ = m(g), m(l)
+    assert tuple(out.shape) == (8, 768) and torch.equal(out[:4], fg) and torch.equal(out[4:], fl_)

@@ -143,3 +143,17 @@ def test_multicrop_wrapper_groups_by_resolution():
     views = [torch.zeros(2, 3, 8, 224, 224)] * 2 + [torch.zeros(2, 3, 8, 96, 96)] * 3
     out = w(views)
     assert calls == [(4, 3, 8, 224, 224), (6, 3, 8, 96, 96)] and tuple(out.shape) == (10, 4)
+
+
+def test_product_code_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package, include/ or the root shim may import or execute it
+    (bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() are the two allowed callers)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "dino-video-summarization-transformer_b200", "**", "*.py"), recursive=True)
+    files += glob.glob(os.path.join(root, "dino-video-summarization-transformer_b200", "csrc", "*.*"))
+    files += [os.path.join(root, "dvst_b200.py")] + glob.glob(os.path.join(root, "include", "*.h"))
+    pat = re.compile(r"dvst_oracle|ref_shim|make_golden|[\"'/]oracle[\"'/]|import oracle|from oracle")
+    bad = [f for f in files if not f.endswith(".so") and pat.search(open(f, errors="ignore").read())]
+    assert len(files) > 15 and not bad, bad

@@ -56,14 +56,24 @@ print("\n".join(out[:14]))
 big = [k for k in per.values() if "gemm_bf16_tn_kernel<2" in k["name"].replace("(int)", "")]
 if big:
     dv = [k for k in per.values() if "dvst" in k["name"]]
+    # the K = 768 deferred-LayerNorm producers (<2, 3, 0, 0> reading < 1.4 GB: A 308 MB + residual 616 MB) are HBM-bound and
+    # reported separately from the tensor-bound launches (bench.py: roofline vs roofline_hbm_gemm)
+    def is_hbm(k):
+        n = k["name"].replace("(int)", "").replace(" ", "")
+        return "gemm_bf16_tn_kernel<2,3,0,0>" in n and k.get("rd", 0.0) < 1.4e9
+    hbm = [k for k in big if is_hbm(k)]
+    ten = [k for k in big if not is_hbm(k)]
+    tb = lambda ks: sum(k.get("rd", 0.0) + k.get("wr", 0.0) for k in ks) / max(len(ks), 1)
     info = {
         "source": f"ncu launch list of `{cmd}` ({os.path.basename(dst)}): cold-cache, serialised; 2-CTA GEMM launches",
-        "gemm_launches": len(big),
-        "dram_bytes_per_launch": sum(k.get("rd", 0.0) + k.get("wr", 0.0) for k in big) / len(big),
+        "gemm_launches": len(ten),
+        "dram_bytes_per_launch": tb(ten),
+        "hbm_gemm_launches": len(hbm),
+        "dram_bytes_per_launch_hbm_gemm": tb(hbm),
         "gemm_share_of_dvst_kernel_time": sum(k.get("us", 0.0) for k in big) / max(sum(k.get("us", 0.0) for k in dv), 1e-9),
         "algorithmic_bytes_note": "per launch the operands + outputs are read / written once (qkv: 308 MB A + 3.5 MB W + "
-                                  "925 MB out; deferred-LayerNorm producers additionally read the 616 MB residual and write "
-                                  "616 MB + the 308 MB bf16 copy)",
+                                  "925 MB out; fc2 producer: 1 233 MB A + 616 MB residual in + 616 MB fp32 + 308 MB bf16 out; "
+                                  "K = 768 producers: 308 MB A + 616 MB in + 924 MB out = 1.85 GB)",
     }
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     json.dump(info, open(os.path.join(root, "profiles", "gemm_traffic.json"), "w"), indent=1)
