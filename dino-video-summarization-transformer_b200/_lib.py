@@ -60,9 +60,11 @@ SIGNATURES = {
                                   c_void_p]),
     "dvst_select_frames": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dvst_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    "dvst_rowstats768": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p]),
+    "dvst_rowstats768": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p]),
+    "dvst_row_offsets768": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "dvst_gemm_bf16_ln": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
-                                  c_float, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+                                  c_float, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int,
+                                  c_void_p]),
     "dvst_knn_similarity": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "dvst_knn_topk": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "dvst_knn_vote": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p,

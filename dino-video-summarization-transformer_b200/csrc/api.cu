@@ -177,18 +177,27 @@ int dvst_preprocess_u8(const unsigned char* video, int n_frames, int H, int W, i
                               static_cast<cudaStream_t>(stream));
 }
 
-int dvst_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M, void* stream) {
+int dvst_row_offsets768(const float* stats, float* xoff, long long M, void* stream) {
+  if (stats == nullptr || xoff == nullptr || (reinterpret_cast<uintptr_t>(stats) & 15))
+    return set_error("dvst_row_offsets768: null or misaligned argument");
+  return launch_row_offsets768(stats, xoff, M, static_cast<cudaStream_t>(stream));
+}
+
+int dvst_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, float* xoff, long long M,
+                     void* stream) {
   if (x == nullptr || xb == nullptr || stats == nullptr) return set_error("dvst_rowstats768: null argument");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (ldx % 4) || (reinterpret_cast<uintptr_t>(xb) & 7) || (ldxb % 4) ||
       (reinterpret_cast<uintptr_t>(stats) & 7))
     return set_error("dvst_rowstats768: misaligned argument");
-  return launch_rowstats768(x, ldx, xb, ldxb, stats, M, static_cast<cudaStream_t>(stream));
+  return launch_rowstats768(x, ldx, xb, ldxb, stats, M, static_cast<cudaStream_t>(stream), xoff);
 }
 
 int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
                       const float* ln_stats, const float* ln_colsum, float ln_eps, float* x_inout, long long ldx,
-                      void* xb, long long ldxb, float* stats_out, void* out, long long ldo, int act, void* stream) {
+                      void* xb, long long ldxb, float* stats_out, const float* xoff, void* out, long long ldo, int act,
+                      void* stream) {
   GemmArgs g;
+  g.xoff = xoff;
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.M = M; g.N = N; g.K = K;
   g.act = act;
   if (x_inout != nullptr) {

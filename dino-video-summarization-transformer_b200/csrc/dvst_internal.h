@@ -45,6 +45,8 @@ struct GemmArgs {
   void* xb = nullptr;                // bf16 [M, ldxb]
   long long ldxb = 0;
   float* stats_out = nullptr;        // fp32 [M, N / 128, 2]
+  // producer: per-row offset m_r; xb = bf16(x - m_r) and the statistics are those of x - m_r (null = 0)
+  const float* xoff = nullptr;
   int act = 0;  // 0 none, 1 GELU(erf)
   int M = 0, N = 0, K = 0;
   int split = 0;
@@ -57,8 +59,11 @@ int launch_layernorm768(const float* x, long long ldx, const float* gamma, const
                         long long rm_group = 0, long long rm_stride = 0, long long rm_offset = 0);
 // xb = bf16(x), stats[row][j] = (sum, sumsq) of columns [128 j, 128 j + 128): the deferred-LayerNorm inputs for rows that
 // no residual GEMM has written yet (CLS rows after embedding).
+// xoff (optional): receives the exact row mean; xb and the statistics are then those of x - mean
 int launch_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M,
-                       cudaStream_t st);
+                       cudaStream_t st, float* xoff = nullptr);
+// xoff[r] += mean of the centred row (sum of the six per-128-column sums / 768): moves the offsets to the current row means
+int launch_row_offsets768(const float* stats, float* xoff, long long M, cudaStream_t st);
 int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,
                     const int* starts, cudaStream_t st);
 int launch_cast_bf16(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off, long long M,

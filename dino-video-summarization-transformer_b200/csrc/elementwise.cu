@@ -83,22 +83,40 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restri
 // Deferred-LayerNorm inputs for rows not produced by a residual GEMM: xb = bf16(x), per-128-column (sum, sumsq).
 __global__ void __launch_bounds__(256) rowstats768_kernel(const float* __restrict__ x, long long ldx,
                                                           __nv_bfloat16* __restrict__ xb, long long ldxb,
-                                                          float* __restrict__ stats, long long M) {
+                                                          float* __restrict__ stats, long long M,
+                                                          float* __restrict__ xoff) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[6];
+  float tot = 0.f;
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {  // one partial per 128 columns = one float4 per lane
-    const int c4 = j * 32 + lane;
-    const float4 v = xr[c4];
-    float s1 = (v.x + v.y) + (v.z + v.w);
-    float s2 = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-    *reinterpret_cast<uint2*>(xb + row * ldxb + c4 * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+  for (int j = 0; j < 6; ++j) {
+    v[j] = xr[j * 32 + lane];
+    tot += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float m = xoff != nullptr ? warp_sum(tot) * (1.0f / D) : 0.f;
+  if (xoff != nullptr && lane == 0) xoff[row] = m;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {  // one partial per 128 columns = one float4 per lane, of the centred values
+    const float4 c = make_float4(v[j].x - m, v[j].y - m, v[j].z - m, v[j].w - m);
+    float s1 = (c.x + c.y) + (c.z + c.w);
+    float s2 = (c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w);
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane == 0) *reinterpret_cast<float2*>(stats + (row * 6 + j) * 2) = make_float2(s1, s2);
+    *reinterpret_cast<uint2*>(xb + row * ldxb + (j * 32 + lane) * 4) = make_uint2(pack2(c.x, c.y), pack2(c.z, c.w));
   }
+}
+
+__global__ void __launch_bounds__(256) row_offsets768_kernel(const float* __restrict__ stats, float* __restrict__ xoff,
+                                                             long long M) {
+  const long long row = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (row >= M) return;
+  const float4* sp = reinterpret_cast<const float4*>(stats) + row * 3;
+  const float4 a0 = __ldg(sp), a1 = __ldg(sp + 1), a2 = __ldg(sp + 2);
+  xoff[row] += (((a0.x + a0.z) + (a1.x + a1.z)) + (a2.x + a2.z)) * (1.0f / D);  // old offset + mean of the centred row
 }
 
 // im2col for Conv2d(k=16, s=16) (PatchEmbed, timesformer.py:201-208): x [B,3,T,H,W] fp32 -> rows (b, n, t) in the
@@ -334,13 +352,21 @@ int launch_layernorm768(const float* x, long long ldx, const float* gamma, const
 }
 
 int launch_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* xoff) {
   if (M <= 0) return 0;
   ProfScope prof(PROF_LAYERNORM, static_cast<double>(M) * D * 6.0, st);
   rowstats768_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(xb), ldxb,
-                                                                        stats, M);
+                                                                        stats, M, xoff);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("rowstats launch failed");
+}
+
+int launch_row_offsets768(const float* stats, float* xoff, long long M, cudaStream_t st) {
+  if (M <= 0) return 0;
+  ProfScope prof(PROF_LAYERNORM, static_cast<double>(M) * 52.0, st);
+  row_offsets768_kernel<<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(stats, xoff, M);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("row_offsets launch failed");
 }
 
 int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,

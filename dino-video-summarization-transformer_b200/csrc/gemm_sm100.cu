@@ -20,6 +20,10 @@
 // `stats[row][128-column block]`; the GEMM that consumes LayerNorm(x) (kLN = 1) then runs on `xb` with gamma folded into W:
 //   LN(x) W^T + b = rstd_r (xb W'^T)[r,c] - rstd_r mean_r colsum(W')[c] + (b + W beta)[c],   W' = bf16(gamma * W)
 // so the stand-alone LayerNorm pass (read 4 B + write 2 B per element) disappears from the block.
+// Row offsets: xb is stored as bf16(x - m_r) with m_r a recent mean of row r (`xoff`, refreshed once per block from the row
+// statistics), and the statistics are those of the centred values x - m_r; LayerNorm is shift invariant, so the consumer
+// needs no change.  bf16 rounding and the E[x^2] - mean^2 variance then act on centred values: rows whose mean is large
+// next to their spread lose nothing (with m_r = 0 the operand error would grow like |mean| / std).
 //
 // `split` mode: A and W hold [hi | lo] bf16 halves along K (lo at column offset K); the K loop then runs the three
 // products hi*hi, hi*lo, lo*hi into the same accumulator (~16 mantissa bits) - the "precision=high" path that
@@ -71,6 +75,7 @@ struct GemmParams {
   const float* ln_colsum;  // kLN: fp32 [N] row sums of the (gamma-folded, bf16-rounded) weight
   float ln_eps;
   float* stats_out;        // producers: fp32 [M, N / 128, 2]
+  const float* xoff;       // producers: per-row offset m_r subtracted before the bf16 rounding and the statistics, or null
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) (nn.GELU default, timesformer.py:37).  erf via Abramowitz-Stegun 7.1.26
@@ -371,6 +376,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t v[32];
           tmem_ld_32x32(trow, v);
           uint64_t s1 = 0ull, s2 = 0ull;  // packed (even, odd column) partial sums
+          const float moff = (p.xoff != nullptr && grow + lane < p.M) ? __ldg(p.xoff + grow + lane) : 0.f;
+          const uint64_t nmoff2 = splat2(-moff);
           float2* stat_row = reinterpret_cast<float2*>(p.stats_out) +
                              (static_cast<long long>(grow + lane) * (2 * p.num_n_blocks) + 2 * n_blk + (col_base >> 7));
 #pragma unroll 1
@@ -402,12 +409,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
               const uint64_t wa = add2(add2(pk2(w[4 * j], w[4 * j + 1]), pk2(b4.x, b4.y)), pk2(r4.x, r4.y));
               const uint64_t wb = add2(add2(pk2(w[4 * j + 2], w[4 * j + 3]), pk2(b4.z, b4.w)), pk2(r4.z, r4.w));
-              s1 = add2(add2(s1, wa), wb);
-              s2 = fma2(wb, wb, fma2(wa, wa, s2));
+              const uint64_t ca = add2(wa, nmoff2), cb = add2(wb, nmoff2);  // centred: bf16 copy and statistics
+              s1 = add2(add2(s1, ca), cb);
+              s2 = fma2(cb, cb, fma2(ca, ca, s2));
               unpk2(wa, w[4 * j], w[4 * j + 1]);
               unpk2(wb, w[4 * j + 2], w[4 * j + 3]);
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(w[4 * j]), "f"(w[4 * j + 1]),
                            "f"(w[4 * j + 2]), "f"(w[4 * j + 3]) : "memory");
+              unpk2(ca, w[4 * j], w[4 * j + 1]);
+              unpk2(cb, w[4 * j + 2], w[4 * j + 3]);
             }
             const uint32_t bbox = bst + (g & 1) * (STG_BUF_BYTES / 2) + brow_off;
 #pragma unroll
@@ -459,7 +469,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const float mean = (((a0.x + a0.z) + (a1.x + a1.z)) + (a2.x + a2.z)) * (1.0f / 768.0f);
           const float var = (((a0.y + a0.w) + (a1.y + a1.w)) + (a2.y + a2.w)) * (1.0f / 768.0f) - mean * mean;
           ln_rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
-          ln_nmr = -ln_rstd * mean;
+          ln_nmr = -ln_rstd * mean;  // (mean and variance of the centred row A was cast from)
         }
       }
       mbar_wait(tfull_bar + 8 * a, aph);
@@ -674,6 +684,7 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   p.num_m_blocks = (g.M + BM * kCG - 1) / (BM * kCG);
   p.num_n_blocks = g.N / BN;
   p.ln_stats = g.ln_stats; p.ln_colsum = g.ln_colsum; p.ln_eps = g.ln_eps; p.stats_out = g.stats_out;
+  p.xoff = g.xoff;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_units = num_sms() / kCG;
   const int units = tiles < max_units ? tiles : max_units;

@@ -62,6 +62,7 @@ struct Workspace {
   float* tmp;  // [rows, 768] fp32 scratch for space_only's frame mean
   void* xb;     // bf16 [M, 768] copy of x (deferred LayerNorm: the A operand of the consuming GEMM)
   float* stats; // fp32 [M, 6, 2] per-128-column (sum, sumsq) of every row of x
+  float* xoff;  // fp32 [M] per-row offsets of xb (xb = bf16(x - xoff)), refreshed once per block
   void* attn_scratch;  // fix-up list of the one-pass spatial softmax
   size_t attn_scratch_bytes;
   size_t total;
@@ -91,6 +92,7 @@ static Workspace carve(const Model& m, void* base, long long B, int T, int gh, i
   const bool fl = m.fused_ln && m.cfg.precision == DVST_PRECISION_BF16;
   w.xb = take(fl ? static_cast<size_t>(M) * D * 2 : 1024);
   w.stats = static_cast<float*>(take(fl ? static_cast<size_t>(M) * 12 * 4 : 1024));
+  w.xoff = static_cast<float*>(take(fl ? static_cast<size_t>(M) * 4 : 1024));
   w.attn_scratch_bytes = m.cfg.attention_type == DVST_ATTN_JOINT
                              ? 0 : static_cast<size_t>(spatial_attention_scratch_bytes(static_cast<int>(B), T, static_cast<int>(N)));
   w.attn_scratch = take(w.attn_scratch_bytes ? w.attn_scratch_bytes : 1024);
@@ -312,7 +314,7 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
     g.A = A; g.lda = K == D ? lda : ldh; g.W = Wt; g.ldw = K; g.bias = bias;
     g.M = static_cast<int>(rows); g.N = D; g.K = K;
     g.residual = w.x + row0 * D; g.ldr = D; g.out = w.x + row0 * D; g.ldo = D; g.out_kind = 3;
-    g.xb = xb + row0 * D; g.ldxb = D; g.stats_out = w.stats + row0 * 12;
+    g.xb = xb + row0 * D; g.ldxb = D; g.stats_out = w.stats + row0 * 12; g.xoff = w.xoff + row0;
     return launch_gemm(g, st);
   };
   // out[row0 .. row0+rows) = act(LayerNorm(x) W^T + b) through the folded form
@@ -330,10 +332,14 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
   DVST_TRY(launch_embed_table(m->pos, m->cfg.pos_grid, m->time_embed, m->cfg.num_frames, w.emb, gh, gw, T, st));
   DVST_TRY(launch_im2col16(x_in, w.a, lda, split, D, B, T, H, W, starts, st));
   DVST_TRY(launch_tile_rows768(w.emb, N * T, w.x, Mt, st));  // x[b, n, t] = pos + time; the GEMM accumulates onto it
-  if (fl) DVST_TRY(gemm_res(w.a, m->pe_w, m->pe_b, 0, Mt, D));
-  else DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.x, w.x, D, 1, 0));
+  if (fl) {
+    // offsets start at 0 for the patch rows (the embedded tokens are centred well enough); the CLS rows get their exact mean
+    if (cudaMemsetAsync(w.xoff, 0, static_cast<size_t>(Mt) * sizeof(float), st) != cudaSuccess)
+      return set_error("dvst_forward_features: cudaMemsetAsync failed");
+    DVST_TRY(gemm_res(w.a, m->pe_w, m->pe_b, 0, Mt, D));
+  } else DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.x, w.x, D, 1, 0));
   DVST_TRY(launch_broadcast_row768(m->cls_pos0, w.x + Mt * D, D, static_cast<int>(n_cls), st));
-  if (fl) DVST_TRY(launch_rowstats768(w.x + Mt * D, D, xb + Mt * D, D, w.stats + Mt * 12, n_cls, st));
+  if (fl) DVST_TRY(launch_rowstats768(w.x + Mt * D, D, xb + Mt * D, D, w.stats + Mt * 12, n_cls, st, w.xoff + Mt));
 
   for (int i = 0; i < m->cfg.depth; ++i) {
     const BlockW& b = m->blocks[i];
@@ -393,6 +399,8 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
     if (att == DVST_ATTN_DIVIDED)
       DVST_TRY(launch_cls_mean(w.cls_acc, static_cast<__nv_bfloat16*>(w.a) + Mt * lda, lda, split, D, B, T, nullptr, st));
     if (fl) {
+      // once per block, right before a producer that rewrites xb and the statistics of every row: offsets <- row means
+      DVST_TRY(launch_row_offsets768(w.stats, w.xoff, M, st));
       DVST_TRY(gemm_res(w.a, b.proj_w, b.proj_b, 0, M, D));
       // MLP (:184)
       DVST_TRY(gemm_ln(b.fc1_wf, b.fc1_sf, b.fc1_bf, 0, M, 4 * D, w.hid, ldh, 1));

@@ -157,11 +157,19 @@ int dvst_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, c
  *   consumer form (ln_stats != NULL, K = 768): out (bf16) = act(rstd (A W^T) - rstd mean colsum + bias) where A = xb,
  *       W = bf16(gamma * weight) row-major [N, 768], ln_colsum[c] = sum_k W[c, k], bias = b + weight beta  and
  *       (mean, rstd) come from ln_stats (eps inside the rsqrt as in nn.LayerNorm).
- * dvst_rowstats768 produces (xb, stats) for rows that no residual GEMM has written (the CLS rows after embedding). */
-int dvst_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M, void* stream);
+ * Row offsets (producer form only; xoff fp32 [M] or NULL = 0): xb = bf16(x - xoff[r]) and the statistics are those of
+ * x - xoff[r]; LayerNorm is shift invariant, so the consumer needs nothing else, and both the bf16 rounding and the
+ * variance act on centred values (rows with |mean| >> std lose nothing).  dvst_row_offsets768 moves xoff[r] to the current
+ * row mean (xoff[r] += mean of the centred row) - call it right before a producer that rewrites the same rows.
+ * dvst_rowstats768 produces (xb, stats, and the exact mean in xoff if given) for rows that no residual GEMM has written
+ * (the CLS rows after embedding). */
+int dvst_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, float* xoff, long long M,
+                     void* stream);
+int dvst_row_offsets768(const float* stats, float* xoff, long long M, void* stream);
 int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
                       const float* ln_stats, const float* ln_colsum, float ln_eps, float* x_inout, long long ldx,
-                      void* xb, long long ldxb, float* stats_out, void* out, long long ldo, int act, void* stream);
+                      void* xb, long long ldxb, float* stats_out, const float* xoff, void* out, long long ldo, int act,
+                      void* stream);
 /* nn.LayerNorm(768, eps) over M rows of fp32 (models/timesformer.py:99,105,112,245).  out_kind as above. */
 int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,
                       int out_kind, long long lo_off, long long M, float eps, void* stream);

@@ -288,15 +288,28 @@ def test_knn_topk_ties_and_edges(dev):
 
 
 # ---- deferred LayerNorm: residual GEMM that also emits bf16(x) + row statistics, and the GEMM that consumes them -------
-def _ln_producer(A, W, bias, x):
+def _ln_producer(A, W, bias, x, xoff=None):
     L = _lib.lib()
     M, K = A.shape
     xb = torch.empty(M, 768, device=A.device, dtype=torch.bfloat16)
     stats = torch.zeros(M, 6, 2, device=A.device)
     _lib.check(L.dvst_gemm_bf16_ln(_lib.ptr(A), A.stride(0), _lib.ptr(W), W.stride(0), _lib.ptr(bias), M, 768, K,
-                                   None, None, 0.0, _lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), None, 0, 0,
-                                   _lib.cur_stream()))
+                                   None, None, 0.0, _lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), _lib.ptr(xoff),
+                                   None, 0, 0, _lib.cur_stream()))
     return xb, stats
+
+
+def _ln_consumer(xb, stats, W, b, gamma, beta, act=0):
+    L = _lib.lib()
+    M, N = xb.shape[0], W.shape[0]
+    wf = (W.double() * gamma.double()[None, :]).float().bfloat16().contiguous()
+    sf = wf.double().sum(1).float().contiguous()
+    bf = (b.double() + W.double() @ beta.double()).float().contiguous()
+    out = torch.empty(M, N, device=xb.device, dtype=torch.bfloat16)
+    _lib.check(L.dvst_gemm_bf16_ln(_lib.ptr(xb), 768, _lib.ptr(wf), 768, _lib.ptr(bf), M, N, 768, _lib.ptr(stats),
+                                   _lib.ptr(sf), 1e-6, None, 0, None, 0, None, None, _lib.ptr(out), N, act,
+                                   _lib.cur_stream()))
+    return out
 
 
 @pytest.mark.parametrize("M,K", [(1, 768), (77, 768), (300, 3072), (4099, 768), (40000, 768), (33000, 3072)])
@@ -307,13 +320,15 @@ def test_deferred_layernorm_producer(dev, M, K):
     bias = torch.randn(768, device=dev)
     x0 = torch.randn(M, 768, device=dev) * 2 + 0.3
     ref = x0.double() + A.double() @ W.double().t() + bias.double()
-    x = x0.clone()
-    xb, stats = _ln_producer(A, W, bias, x)
-    assert _rel(x, ref) < 1e-5                      # in-place fp32 residual stream
-    assert torch.equal(xb, x.bfloat16())            # the bf16 copy is the rounding of exactly what was stored
-    blocks = x.double().view(M, 6, 128)
-    assert torch.allclose(stats[:, :, 0].double(), blocks.sum(-1), rtol=1e-5, atol=1e-3)
-    assert torch.allclose(stats[:, :, 1].double(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-3)
+    for xoff in (None, torch.randn(M, device=dev) * 0.5 + 0.3):
+        x = x0.clone()
+        xb, stats = _ln_producer(A, W, bias, x, xoff)
+        assert _rel(x, ref) < 1e-5                      # in-place fp32 residual stream
+        off = 0.0 if xoff is None else xoff[:, None]
+        assert torch.equal(xb, (x - off).bfloat16())    # the bf16 copy is the rounding of exactly what was stored, centred
+        blocks = (x - off).double().view(M, 6, 128)
+        assert torch.allclose(stats[:, :, 0].double(), blocks.sum(-1), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(stats[:, :, 1].double(), (blocks * blocks).sum(-1), rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("M,N,act", [(1, 2304, 0), (130, 3072, 1), (4099, 2304, 0), (40000, 3072, 1), (40000, 1536, 0)])
@@ -326,23 +341,57 @@ def test_deferred_layernorm_consumer(dev, M, N, act):
     beta = torch.randn(768, device=dev) * 0.1
     W = torch.randn(N, 768, device=dev) * 0.04
     b = torch.randn(N, device=dev) * 0.1
-    xb = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
-    stats = torch.empty(M, 6, 2, device=dev)
-    _lib.check(L.dvst_rowstats768(_lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), M, _lib.cur_stream()))
-    assert torch.equal(xb, x.bfloat16())
-    assert torch.allclose(stats[:, :, 0].double(), x.double().view(M, 6, 128).sum(-1), rtol=1e-5, atol=1e-3)
-    wf = (W.double() * gamma.double()[None, :]).float().bfloat16().contiguous()
-    sf = wf.double().sum(1).float().contiguous()
-    bf = (b.double() + W.double() @ beta.double()).float().contiguous()
-    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    _lib.check(L.dvst_gemm_bf16_ln(_lib.ptr(xb), 768, _lib.ptr(wf), 768, _lib.ptr(bf), M, N, 768, _lib.ptr(stats),
-                                   _lib.ptr(sf), 1e-6, None, 0, None, 0, None, _lib.ptr(out), N, act,
-                                   _lib.cur_stream()))
     ref = torch.nn.functional.layer_norm(x.double(), (768,), gamma.double(), beta.double(), 1e-6) @ W.double().t() + b.double()
     if act:
         ref = torch.nn.functional.gelu(ref)
-    # same error budget as LayerNorm -> bf16 -> GEMM -> bf16: operand and output rounding
-    assert _rel(out.float(), ref) < 6e-3
+    for centred in (False, True):
+        xb = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+        stats = torch.empty(M, 6, 2, device=dev)
+        xoff = torch.empty(M, device=dev) if centred else None
+        _lib.check(L.dvst_rowstats768(_lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), _lib.ptr(xoff), M,
+                                      _lib.cur_stream()))
+        c = x - (x.mean(1, keepdim=True) if centred else 0.0)
+        if centred:
+            assert torch.allclose(xoff, x.mean(1), rtol=1e-5, atol=1e-5)
+        assert (xb.float() - c).abs().max() <= 2.0 ** -8 * c.abs().max()
+        assert torch.allclose(stats[:, :, 0].double(), c.double().view(M, 6, 128).sum(-1), rtol=1e-4, atol=2e-2)
+        out = _ln_consumer(xb, stats, W, b, gamma, beta, act)
+        # same error budget as LayerNorm -> bf16 -> GEMM -> bf16: operand and output rounding
+        assert _rel(out.float(), ref) < 6e-3
+
+
+def test_deferred_layernorm_row_offsets_keep_large_mean_rows_accurate(dev):
+    """Rows whose mean is 50x their spread: with zero offsets the bf16 copy (rounding relative to |x|) and the
+    E[x^2] - mean^2 variance lose the signal; with the offsets moved to the row means (dvst_row_offsets768 between two
+    producers) the producer / consumer pair is as accurate as LayerNorm -> bf16 -> GEMM."""
+    torch.manual_seed(3)
+    L = _lib.lib()
+    M, K, N = 4099, 768, 2304
+    A = torch.randn(M, K, device=dev).bfloat16()
+    Wp = (torch.randn(768, K, device=dev) * 0.03).bfloat16()
+    bias = torch.randn(768, device=dev) * 0.1
+    x0 = torch.randn(M, 768, device=dev) + 50.0 * torch.randn(M, 1, device=dev).sign()
+    gamma = torch.randn(768, device=dev) * 0.1 + 1.0
+    beta = torch.randn(768, device=dev) * 0.1
+    W = torch.randn(N, 768, device=dev) * 0.04
+    b = torch.randn(N, device=dev) * 0.1
+    xnew = x0.double() + A.double() @ Wp.double().t() + bias.double()
+    ref = torch.nn.functional.layer_norm(xnew, (768,), gamma.double(), beta.double(), 1e-6) @ W.double().t() + b.double()
+    # zero offsets: inaccurate (documents why the offsets exist)
+    x = x0.clone()
+    xb, stats = _ln_producer(A, Wp, bias, x, None)
+    bad = _rel(_ln_consumer(xb, stats, W, b, gamma, beta).float(), ref)
+    # offsets = means of the previous version of the rows (what the forward does once per block)
+    xoff = torch.zeros(M, device=dev)
+    xb0 = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+    st0 = torch.empty(M, 6, 2, device=dev)
+    _lib.check(L.dvst_rowstats768(_lib.ptr(x0), 768, _lib.ptr(xb0), 768, _lib.ptr(st0), None, M, _lib.cur_stream()))
+    _lib.check(L.dvst_row_offsets768(_lib.ptr(st0), _lib.ptr(xoff), M, _lib.cur_stream()))
+    assert torch.allclose(xoff, x0.mean(1), rtol=1e-4, atol=1e-3)
+    x = x0.clone()
+    xb, stats = _ln_producer(A, Wp, bias, x, xoff)
+    good = _rel(_ln_consumer(xb, stats, W, b, gamma, beta).float(), ref)
+    assert good < 6e-3 and bad > 5 * good, (good, bad)
 
 
 @pytest.mark.parametrize("mode,B,T,N,adversarial", [(1, 2, 3, 196, False), (3, 2, 2, 196, False), (1, 1, 2, 36, False),

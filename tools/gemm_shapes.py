@@ -30,7 +30,7 @@ for (M, K, name) in [(200768, 3072, "fc2 producer (res + xb + stats)"), (200704,
     bias = torch.randn(768, device=dev); x = torch.randn(M, 768, device=dev)
     xb = torch.empty(M, 768, device=dev, dtype=torch.bfloat16); stats = torch.empty(M, 6, 2, device=dev)
     f = lambda: _lib.check(L.dvst_gemm_bf16_ln(_lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(bias), M, 768, K, None, None, 0.0,
-                                               _lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), None, 0, 0,
+                                               _lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), None, None, 0, 0,
                                                _lib.cur_stream()))
     for _ in range(3): f()
     torch.cuda.synchronize()
@@ -46,7 +46,7 @@ for (M, N, act, name) in [(200704, 2304, 0, "qkv consumer (kLN)"), (200768, 3072
     stats = torch.rand(M, 6, 2, device=dev) * 50 + 150
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     f = lambda: _lib.check(L.dvst_gemm_bf16_ln(_lib.ptr(xb), 768, _lib.ptr(W), 768, _lib.ptr(bias), M, N, 768,
-                                               _lib.ptr(stats), _lib.ptr(sf), 1e-6, None, 0, None, 0, None, _lib.ptr(out),
+                                               _lib.ptr(stats), _lib.ptr(sf), 1e-6, None, 0, None, 0, None, None, _lib.ptr(out),
                                                N, act, _lib.cur_stream()))
     for _ in range(3): f()
     torch.cuda.synchronize()
