@@ -92,7 +92,9 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // state (m, l un-reduced over the quad, un-normalised o).
 // SPLIT: q/k/v come as bf16 hi/lo pairs (qb = Q lo fragments, K / V lo rows at + lo_delta); every product is evaluated
 // as hi*hi + hi*lo + lo*hi and P is split the same way, ~16 mantissa bits end to end.
-template <bool SPLIT>
+// MAXP: compile-time bound on the 16-key tile pairs of a block (4 = the general 64-key block; 1 / 2 for sequences of at
+// most 16 / 32 keys - temporal attention - where the general form would run its softmax over 48 / 32 padded keys).
+template <bool SPLIT, int MAXP = 4>
 __device__ __forceinline__ void attn_block(const uint32_t (&qa)[4][4], const uint32_t (&qb)[4][4], uint32_t sKb,
                                            uint32_t sVb, uint32_t lo_delta, int pitch, int key0, int S,
                                            int ntile_pairs, bool first, int lane, float (&o)[8][4], float& m0,
@@ -100,14 +102,15 @@ __device__ __forceinline__ void attn_block(const uint32_t (&qa)[4][4], const uin
   const int tig = lane & 3;
   const float scale_log2 = 0.125f * 1.4426950408889634f;
   const int mat = lane >> 3, r = lane & 7;
-  float s[8][4];
+  constexpr int NT = 2 * MAXP;
+  float s[NT][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-  // ---- S = Q K^T : k-step outer so the 8 accumulator chains are independent ----
+  for (int i = 0; i < NT; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+  // ---- S = Q K^T : k-step outer so the accumulator chains are independent ----
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {
+    for (int np = 0; np < MAXP; ++np) {
       if (np < ntile_pairs) {
         const int row = np * 16 + (mat >> 1) * 8 + r;
         const int ch = kk * 2 + (mat & 1);
@@ -128,16 +131,16 @@ __device__ __forceinline__ void attn_block(const uint32_t (&qa)[4][4], const uin
   }
   // ---- mask + online softmax ----
   float mx0 = -INFINITY, mx1 = -INFINITY;
-  if (key0 + 64 > S) {  // only the last key block can hold padded keys
+  if (key0 + 16 * MAXP > S) {  // only the last key block can hold padded keys
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       const int c = key0 + nt * 8 + tig * 2;
       if (c >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
       if (c + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
     }
   }
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
+  for (int nt = 0; nt < NT; ++nt) {
     mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
     mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
   }
@@ -151,7 +154,7 @@ __device__ __forceinline__ void attn_block(const uint32_t (&qa)[4][4], const uin
   const float off0 = mn0 * scale_log2, off1 = mn1 * scale_log2;
   float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
+  for (int nt = 0; nt < NT; ++nt) {
     s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2, -off0));
     s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2, -off0));
     s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2, -off1));
@@ -167,7 +170,7 @@ __device__ __forceinline__ void attn_block(const uint32_t (&qa)[4][4], const uin
   }
   // ---- O += P V ----
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = 0; kk < MAXP; ++kk) {
     if (kk < ntile_pairs) {
       const uint32_t a0 = pack2(s[2 * kk][0], s[2 * kk][1]), a1 = pack2(s[2 * kk][2], s[2 * kk][3]);
       const uint32_t a2 = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
@@ -199,7 +202,7 @@ __device__ __forceinline__ void attn_block(const uint32_t (&qa)[4][4], const uin
 
 // One 16-query tile against all S keys staged in shared memory (rows at sK + key * pitch).  Leaves the UN-normalised
 // output in o[8][4] and the quad-reduced row sums in l0 / l1.
-template <bool SPLIT>
+template <bool SPLIT, int MAXP = 4>
 __device__ __forceinline__ void attn_tile(const uint32_t (&qa)[4][4], const uint32_t (&qb)[4][4], uint32_t sK,
                                           uint32_t sV, uint32_t lo_delta, int pitch, int S, int S_pad, int lane,
                                           float (&o)[8][4], float& l0, float& l1) {
@@ -210,8 +213,8 @@ __device__ __forceinline__ void attn_tile(const uint32_t (&qa)[4][4], const uint
   const int n_kblocks = (S + 63) >> 6;
   for (int kb = 0; kb < n_kblocks; ++kb) {
     const int key0 = kb * 64;
-    attn_block<SPLIT>(qa, qb, sK + key0 * pitch, sV + key0 * pitch, lo_delta, pitch, key0, S,
-                      min(4, (S_pad - key0) >> 4), kb == 0, lane, o, m0, m1, l0, l1);
+    attn_block<SPLIT, MAXP>(qa, qb, sK + key0 * pitch, sV + key0 * pitch, lo_delta, pitch, key0, S,
+                            min(MAXP, (S_pad - key0) >> 4), kb == 0, lane, o, m0, m1, l0, l1);
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -456,7 +459,9 @@ __global__ void __launch_bounds__(128, 3) temporal_attention_kernel(const AttnPa
       ldsm_x4(sQ + row * TROW + ((ch ^ (row & 7)) << 4), qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3]);
     }
     float o[8][4], l0, l1;
-    attn_tile<false>(qa, qa, sK, sV, 0, TROW, T, T_pad, lane, o, l0, l1);
+    if (T_pad == 16) attn_tile<false, 1>(qa, qa, sK, sV, 0, TROW, T, T_pad, lane, o, l0, l1);
+    else if (T_pad == 32) attn_tile<false, 2>(qa, qa, sK, sV, 0, TROW, T, T_pad, lane, o, l0, l1);
+    else attn_tile<false, 4>(qa, qa, sK, sV, 0, TROW, T, T_pad, lane, o, l0, l1);
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     __syncwarp();  // every lane has its Q fragments of this tile: the Q rows may now be overwritten
 #pragma unroll
