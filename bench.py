@@ -106,7 +106,9 @@ def main_reference(args):
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    # started BEFORE the warm-up (nvidia-smi needs ~0.3 s to deliver its first sample); samples are then filtered to the
+    # timed window by their timestamps
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -119,7 +121,8 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_start=None, t_end=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -131,6 +134,15 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
+        if t_start is not None and t_end is not None:
+            def ts(r):
+                try:
+                    return datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except Exception:
+                    return None
+            inside = [r for r in rows if ts(r) is not None and t_start <= ts(r) <= t_end + 0.05]
+            if len(inside) >= 2:
+                rows = inside
         sm, reasons, mx, pw = [], set(), None, []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -211,26 +223,28 @@ def main_ours(args):
             torch.cuda.synchronize()
 
     # ---- device-resident timing (`value`) ----
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])) if rank == 0 else None
     for i in range(args.warmup):
         step(dev_clips[i % 2])
     sync_all()
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])) if rank == 0 else None
     _lib.profile_enable(True)
     _lib.profile_collect()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    wall0 = time.time()
     e0.record()
     for i in range(args.steps):
         out = step(dev_clips[i % 2])
     e1.record()
     sync_all()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
     prof = _lib.profile_collect()
     _lib.profile_enable(False)
-    clocks = sampler.stop() if sampler is not None else None
+    clocks = sampler.stop(wall0, wall1) if sampler is not None else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
