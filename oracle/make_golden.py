@@ -189,7 +189,7 @@ def gen_driver(models):
     ds = R["dino_similarity"]
     dll = R["dino_loss_loader"]
     sd = synth_backbone_state_dict(0, depth=12, num_frames=8)
-    vids = {"vidA": 24, "vidB": 13}  # unsampled frame counts -> F = 6 and 4 sampled frames at rate 4
+    vids = {"vidA": 24, "vidB": 13, "vidC": 137}  # unsampled frame counts -> F = 6, 4 and 35 sampled frames at rate 4 (35 > 30: sliding teacher windows)
     raw = {}
     for i, (k, n) in enumerate(vids.items()):
         g = torch.Generator().manual_seed(300 + i)
