@@ -16,8 +16,28 @@ def _n(g, *shape, std=0.02, mean=0.0):
 
 
 def synth_backbone_state_dict(seed=0, depth=12, num_frames=8, img_size=224, attention_type="divided_space_time",
-                              num_classes=0):
-    """State dict with the reference VisionTransformer's keys (models/timesformer.py:212-252)."""
+                              num_classes=0, hard=False):
+    """State dict with the reference VisionTransformer's keys (models/timesformer.py:212-252).
+    hard=True mimics what trained ViT checkpoints do to the numerics: sharp attention (large q / k projections), LayerNorm
+    gains up to ~3, a residual-stream channel carrying a massive activation and a common offset on every token (rows whose
+    mean is several times their spread) - the regimes that stress bf16 operands, the deferred LayerNorm and the one-pass
+    softmax."""
+    sd = _synth_backbone(seed, depth, num_frames, img_size, attention_type, num_classes)
+    if hard:
+        g = torch.Generator().manual_seed(seed + 7919)
+        for k in list(sd):
+            if k.endswith("qkv.weight"):
+                sd[k] = sd[k] * 1.5                                   # logits ~2.3x larger: sharp attention rows
+            elif ".norm" in k and k.endswith(".weight") or k.endswith("temporal_norm1.weight"):
+                sd[k] = sd[k] * (1.0 + 2.0 * torch.rand(sd[k].shape, generator=g))
+        sd["patch_embed.proj.bias"] = sd["patch_embed.proj.bias"] + 2.0   # common offset on every token
+        sd["patch_embed.proj.bias"][5] += 40.0                            # a massive-activation channel
+        for i in range(depth):
+            sd[f"blocks.{i}.mlp.fc2.bias"] = sd[f"blocks.{i}.mlp.fc2.bias"] + 0.3
+    return sd
+
+
+def _synth_backbone(seed, depth, num_frames, img_size, attention_type, num_classes):
     g = torch.Generator().manual_seed(seed)
     P = (img_size // 16) ** 2
     sd = {
