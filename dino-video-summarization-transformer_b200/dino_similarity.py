@@ -312,7 +312,11 @@ def dino_similarity(cfg, local_clip_size, global_clip_size, sampling_rate, file_
     if dataset is None:
         raise ValueError("pass `dataset`: an iterable of (frames, file_name); video decoding is not part of this path")
     if model is None:
-        model = get_vit_base_patch16_224(cfg=cfg, no_head=False)
+        # Mode R (the reference's own loss: 768-d features, tau_t = 0.02) amplifies feature error ~50x, so the model the
+        # driver builds for it runs in precision="high" (per-frame loss within 1e-3 of the reference); mode H (a
+        # HeadScorer) meets the same bound with bf16 operands.  DVST_PRECISION overrides; a model passed in keeps its own.
+        prec = os.environ.get("DVST_PRECISION") or ("high" if scorer is None else "bf16")
+        model = get_vit_base_patch16_224(cfg=cfg, no_head=False, precision=prec)
         if getattr(cfg, "pretrained_weights", None):
             ckpt = torch.load(cfg.pretrained_weights, map_location="cpu")
             renamed = {x[len("backbone."):]: y for x, y in ckpt.items() if x.startswith("backbone.")}
