@@ -400,3 +400,17 @@ def test_full_size_long_clip_and_knn_view_shapes(dev):
         out = w([g, l])
         fg, fl_ = m(g), m(l)
     assert tuple(out.shape) == (8, 768) and torch.equal(out[:4], fg) and torch.equal(out[4:], fl_)
+
+
+def test_pipeline_tool_single_gpu(dev, tmp_path):
+    """tools/pipeline_demo.py: uint8 upload -> fused preprocess -> batched scoring -> gather -> JSON -> device selection,
+    with its own --check (every video recomputed alone: bit-identical losses, identical index lists).  The same command
+    under torchrun --nproc-per-node 2 (NCCL) writes the identical file (verified on 2 B200s; not repeated here)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "pipeline_demo.py"), "--videos", "6", "--depth", "2",
+                          "--out", str(tmp_path / "loss.json"), "--check"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    d = json.load(open(tmp_path / "loss.json"))
+    assert len(d) == 6 and len(d["video_0000"]) == 30   # the 2-frame video takes the reference's dummy path
