@@ -15,7 +15,7 @@
 //
 // One-pass softmax (kOnePass, used when the caller provides scratch): softmax is invariant to the reference point, and any
 // reference within ~44 nats of the row maximum keeps every exp2 and the fp32 / bf16 sums in range, so the reference is
-// the maximum of the FIRST 32 keys only (one TMEM round trip instead of a full pass over S).  A row whose exponentials
+// the maximum of the FIRST 32 keys and the CLS key only (one TMEM round trip instead of a full pass over S).  A row whose exponentials
 // still grow past 2^64 (its maximum lies > 44 nats above those 32 keys) is appended to a fix-up list, and
 // attention_fixup_kernel recomputes exactly those rows in fp32 from the packed qkv afterwards - results stay exact for
 // every input, the common case pays nothing.
@@ -299,11 +299,19 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
         const int b = seq / p.T, t = seq - b * p.T;
         mbar_wait(sfull_bar + 8 * tile, tp);
         tc_fence_after();
-        // ---- pass 1: row max (one-pass softmax: of the first 32 keys only) ----
+        // ---- pass 1: row max (one-pass softmax: of the first 32 keys and the CLS key only) ----
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         {
           uint32_t v[32], v2[32];
           tmem_ld_32x32(treg, v);
+          if constexpr (kOnePass) {
+            // ... plus the CLS key (token N): heads that use CLS as an attention sink put their row maximum there, and
+            // the single extra column rides in the same TMEM round trip
+            uint32_t sc;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(sc) : "r"(treg + N) : "memory");
+            tmem_ld_wait();
+            mx4[3] = __uint_as_float(sc);
+          }
 #pragma unroll
           for (int c = 0; c < (kOnePass ? 1 : 8); ++c) {
             if (c < nch) {

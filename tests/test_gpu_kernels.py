@@ -395,7 +395,8 @@ def test_deferred_layernorm_row_offsets_keep_large_mean_rows_accurate(dev):
 
 
 @pytest.mark.parametrize("mode,B,T,N,adversarial", [(1, 2, 3, 196, False), (3, 2, 2, 196, False), (1, 1, 2, 36, False),
-                                                     (1, 2, 3, 196, True), (3, 1, 2, 196, True), (1, 1, 2, 36, True)])
+                                                     (1, 2, 3, 196, True), (3, 1, 2, 196, True), (1, 1, 2, 36, True),
+                                                     (1, 2, 2, 196, "sink"), (3, 1, 2, 196, "sink")])
 def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
     """tcgen05 spatial attention with scratch: softmax referenced to the maximum of the first 32 keys.  Ordinary inputs
     need no fix-up; adversarial ones (row maxima hundreds of nats above those 32 keys: exp2 overflows) are recomputed
@@ -405,7 +406,14 @@ def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
     Mt = B * N * T
     ncls = B * T if mode == 3 else B
     qkv = (torch.randn(Mt + ncls, 2304, device=dev) * 1.5).bfloat16()
-    if adversarial:
+    if adversarial == "sink":
+        # every query sees the CLS key ~75 nats above all other keys (an attention-sink head): the CLS key is part of the
+        # softmax reference, so no row needs the fix-up
+        u = torch.nn.functional.normalize(torch.randn(64, device=dev), dim=0)
+        for h in range(12):
+            qkv[:, h * 64: (h + 1) * 64] += (20.0 * u).bfloat16()
+            qkv[Mt:, 768 + h * 64: 768 + (h + 1) * 64] = (30.0 * u).bfloat16()
+    elif adversarial:
         # keys whose position inside the frame is >= 40 (and the CLS keys) point along u with a large norm; every third
         # query does too -> scores ~ +-2000 / 8 far above anything among the first 32 keys
         u = torch.nn.functional.normalize(torch.randn(64, device=dev), dim=0)
@@ -423,7 +431,7 @@ def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
     _lib.check(L.dvst_attention_ws(_lib.ptr(qkv), 2304, _lib.ptr(out), 768, _lib.ptr(cls_out), mode, B, T, N, Mt,
                                    _lib.ptr(scratch), nb, _lib.cur_stream()))
     n_fix = int(scratch[:4].view(torch.int32)[0])
-    assert (n_fix > 0) == adversarial
+    assert (n_fix > 0) == (adversarial is True)
     q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
     refo = torch.zeros(Mt + ncls, 768, device=dev)
     refc = torch.zeros(B, T, 768, device=dev)
