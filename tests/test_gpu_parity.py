@@ -414,3 +414,27 @@ def test_pipeline_tool_single_gpu(dev, tmp_path):
     assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
     d = json.load(open(tmp_path / "loss.json"))
     assert len(d) == 6 and len(d["video_0000"]) == 30   # the 2-frame video takes the reference's dummy path
+
+
+def test_forward_is_cuda_graph_capturable(dev):
+    """The C ABI promises no device synchronisation and no device allocation inside a call (include/dvst.h): a whole
+    forward (146 launches for ViT-B) can therefore be captured into a CUDA graph and replayed - the way to run small,
+    launch-bound batches.  The replay on new input equals the eager call bit for bit."""
+    m = build(dev, 1, 2)
+    x = synth_clips(70, 2, 3).to(dev)
+    x2 = synth_clips(71, 2, 3).to(dev)
+    with torch.no_grad():
+        ref2 = m(x2).clone()
+        m(x)                                            # weights packed, workspace allocated, kernel attributes set
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m(x)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = m(x)
+        x.copy_(x2)
+        g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out, ref2)
