@@ -394,9 +394,9 @@ def test_deferred_layernorm_row_offsets_keep_large_mean_rows_accurate(dev):
     assert good < 6e-3 and bad > 5 * good, (good, bad)
 
 
-@pytest.mark.parametrize("mode,B,T,N,adversarial", [(1, 2, 3, 196, False), (3, 2, 2, 196, False), (1, 1, 2, 36, False),
-                                                     (1, 2, 3, 196, True), (3, 1, 2, 196, True), (1, 1, 2, 36, True),
-                                                     (1, 2, 2, 196, "sink"), (3, 1, 2, 196, "sink")])
+@pytest.mark.parametrize("mode,B,T,N,adversarial", [(1, 5, 5, 196, False), (3, 5, 5, 196, False), (1, 5, 5, 36, False),
+                                                     (1, 5, 5, 196, True), (3, 5, 5, 196, True), (1, 5, 5, 36, True),
+                                                     (1, 5, 5, 196, "sink"), (3, 5, 5, 196, "sink"), (1, 1, 2, 196, False)])
 def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
     """tcgen05 spatial attention with scratch: softmax referenced to the maximum of the first 32 keys.  Ordinary inputs
     need no fix-up; adversarial ones (row maxima hundreds of nats above those 32 keys: exp2 overflows) are recomputed
@@ -431,7 +431,8 @@ def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
     _lib.check(L.dvst_attention_ws(_lib.ptr(qkv), 2304, _lib.ptr(out), 768, _lib.ptr(cls_out), mode, B, T, N, Mt,
                                    _lib.ptr(scratch), nb, _lib.cur_stream()))
     n_fix = int(scratch[:4].view(torch.int32)[0])
-    assert (n_fix > 0) == (adversarial is True)
+    # (launches with fewer than 2 x #SM problems keep the two-pass softmax: nothing is listed there)
+    assert (n_fix > 0) == (adversarial is True and B * T * 12 >= 296)
     q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
     refo = torch.zeros(Mt + ncls, 768, device=dev)
     refc = torch.zeros(B, T, 768, device=dev)
