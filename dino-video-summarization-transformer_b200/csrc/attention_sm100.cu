@@ -580,9 +580,10 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
     cur = smem;
   }
   // one-pass softmax needs the fix-up list: counter at scratch[0], entries from scratch + 256
-  // (small launches are latency bound: there the memset + fix-up launches cost more than the max pass they replace)
+  // (the choice must not depend on the batch size: one- and two-pass results differ in the last bits, and a clip's features
+  // are promised to be independent of what else is in its batch)
   const bool one_pass = g_attention_impl == 1 && scratch != nullptr && scratch_bytes >= spatial_attention_scratch_bytes(B, T, N) &&
-                        (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && p.n_prob >= 2 * num_sms();
+                        (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
   p.fix_count = static_cast<int*>(scratch);
   p.fix_list = reinterpret_cast<int2*>(static_cast<uint8_t*>(scratch) + 256);
   const uint64_t BN = static_cast<uint64_t>(B) * N;

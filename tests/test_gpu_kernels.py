@@ -431,8 +431,7 @@ def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
     _lib.check(L.dvst_attention_ws(_lib.ptr(qkv), 2304, _lib.ptr(out), 768, _lib.ptr(cls_out), mode, B, T, N, Mt,
                                    _lib.ptr(scratch), nb, _lib.cur_stream()))
     n_fix = int(scratch[:4].view(torch.int32)[0])
-    # (launches with fewer than 2 x #SM problems keep the two-pass softmax: nothing is listed there)
-    assert (n_fix > 0) == (adversarial is True and B * T * 12 >= 296)
+    assert (n_fix > 0) == (adversarial is True)
     q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
     refo = torch.zeros(Mt + ncls, 768, device=dev)
     refc = torch.zeros(B, T, 768, device=dev)
