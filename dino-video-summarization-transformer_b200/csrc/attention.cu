@@ -743,6 +743,13 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
     if (rc != 1) return rc;
     rc = 0;
   }
+  if (!split && mode == 2) {
+    // joint space-time attention: flash-style tcgen05 kernel (attention_sm100.cu)
+    rc = launch_joint_attention_sm100(qkv, ld, out, ldo, B, N * T, cls_base, st);
+    if (rc == 0) { count_launch(); return 0; }
+    if (rc != 1) return rc;
+    rc = 0;
+  }
   if (mode == 0 && S_pad <= 48 && !split) {
     // contiguous-sequence kernel
     const size_t smem = static_cast<size_t>(S_pad) * TROW;

@@ -610,4 +610,415 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
   return e == cudaSuccess ? 0 : set_error("attention(sm100) launch: %s", cudaGetErrorString(e));
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Long sequences - joint space-time attention (models/timesformer.py:120-123 with attention_type = 'joint_space_time'):
+// 1 + N*T tokens per clip (6 273 at T = 32), 57 % of the model's FLOPs.  Flash-style on tcgen05: a persistent CTA takes a
+// (clip, head, block of 256 queries) problem, keeps the two 128-row Q tiles in shared memory and streams the clip's K / V
+// in 128-key tiles through a 4-stage TMA ring.  Per key tile and Q tile:
+//   S = Q K^T (128 x 128 x 64, TMEM) -> online softmax, one thread per query row (running max m, running sum l; when a
+//   row's max grows, its O accumulator is rescaled in TMEM with tcgen05.ld / tcgen05.st - the warp does that only if one of
+//   its rows needs it) -> P (bf16) written over S -> O += P V (A = P from TMEM, V MN-major from shared memory).
+// The tokens of a clip are contiguous rows (patch tokens b*NT .. b*NT + NT - 1) plus the clip's CLS row, kept as the LAST
+// token (attention does not depend on the key order): every tile is one 2-D TMA box, except the last one, which is a
+// shorter box (NT % 128 rows) plus a 128-byte copy of the CLS row; its padding keys are masked.
+// tcgen05.mma instructions of one thread execute in order, so "S of the next key tile complete" (what the softmax warps
+// wait for) implies "P V of the previous tile complete": the O rescale needs no barrier of its own.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int JT_STAGES = 4;
+constexpr int JT_TILE = 128 * 128;  // bytes of one 128-row x 64-column bf16 tile
+
+struct JtParams {
+  const __nv_bfloat16* qkv;
+  long long ld;
+  __nv_bfloat16* out;
+  long long ldo;
+  int NT, S;        // patch tokens per clip; sequence length NT + 1 (CLS = token NT)
+  int rem;          // NT % 128: patch rows of the last tile (the CLS row follows them)
+  int n_tiles;      // 128-token tiles per clip = NT / 128 + 1
+  int n_qblk;       // query blocks (two tiles) per (clip, head)
+  int n_prob, heads;
+  long long cls_base;
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const __grid_constant__ CUtensorMap tmRem,
+                             const __grid_constant__ CUtensorMap tmOutFull, const __grid_constant__ CUtensorMap tmOutRem,
+                             const JtParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t sQ = base;                                   // 2 tiles
+  const uint32_t sKV = base + 2 * JT_TILE;                    // JT_STAGES x {K tile, V tile}
+  const uint32_t sO = sKV + JT_STAGES * 2 * JT_TILE;          // 2 output staging tiles
+  const uint32_t bars = sO + 2 * JT_TILE;
+  const uint32_t q_full = bars, q_empty = bars + 8;
+  const uint32_t kv_full = bars + 16;                         // [JT_STAGES]
+  const uint32_t kv_empty = kv_full + 8 * JT_STAGES;          // [JT_STAGES]
+  const uint32_t s_full = kv_empty + 8 * JT_STAGES;           // [2]
+  const uint32_t p_full = s_full + 16;                        // [2]
+  const uint32_t o_full = p_full + 16;                        // [2]
+  const uint32_t o_empty = o_full + 16;                       // [2]
+  const uint32_t tmem_slot = o_empty + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmFull);
+    tma_prefetch_desc(&tmRem);
+    tma_prefetch_desc(&tmOutFull);
+    tma_prefetch_desc(&tmOutRem);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < JT_STAGES; ++s) {
+      mbar_init(kv_full + 8 * s, 1);
+      mbar_init(kv_empty + 8 * s, 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(s_full + 8 * t, 1);
+      mbar_init(p_full + 8 * t, 4);
+      mbar_init(o_full + 8 * t, 1);
+      mbar_init(o_empty + 8 * t, 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  // stale rows of partial tiles are multiplied by P = 0 (keys) or never stored (queries): they must be finite
+  for (uint32_t i = threadIdx.x; i < (2 + 2 * JT_STAGES) * JT_TILE / 16; i += NUM_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int n_tiles = p.n_tiles;
+  auto decode = [&](int prob, int& b, int& head, int& qb) {
+    qb = prob % p.n_qblk;
+    const int bh = prob / p.n_qblk;
+    head = bh % p.heads;
+    b = bh / p.heads;
+  };
+
+  if (warp == 0) {
+    // ===== producer =====
+    // one token tile (tile index t of clip b, column offset col) -> dst; returns the TMA bytes to expect
+    auto load_tile = [&](uint32_t dst, uint32_t bar, int b, int t, int col) -> uint32_t {
+      if (t >= n_tiles) return 0u;                       // inactive second Q tile of the last block
+      const int row0 = b * p.NT + t * 128;
+      if (t < n_tiles - 1) {
+        if (lane == 0) tma_load_2d(dst, &tmFull, bar, col, row0);
+        return JT_TILE;
+      }
+      if (p.rem > 0 && lane == 0) tma_load_2d(dst, &tmRem, bar, col, row0);
+      if (lane < 8) {                                    // the CLS row behind the last patch rows
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.qkv + (p.cls_base + b) * p.ld + col) + lane);
+        *reinterpret_cast<uint4*>(smem + (dst - base) + p.rem * 128 + ((lane ^ (p.rem & 7)) << 4)) = v;
+      }
+      return static_cast<uint32_t>(p.rem) * 128u;
+    };
+    uint32_t it_kv = 0;
+    int pi = 0;
+    for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++pi) {
+      int b, head, qb;
+      decode(prob, b, head, qb);
+      if (lane == 0) mbar_wait(q_empty, (pi & 1) ^ 1);
+      __syncwarp();
+      uint32_t bytes = load_tile(sQ, q_full, b, 2 * qb, head * HD);
+      bytes += load_tile(sQ + JT_TILE, q_full, b, 2 * qb + 1, head * HD);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(q_full, bytes);
+      for (int j = 0; j < n_tiles; ++j, ++it_kv) {
+        const int s = it_kv % JT_STAGES;
+        if (lane == 0) mbar_wait(kv_empty + 8 * s, ((it_kv / JT_STAGES) & 1) ^ 1);
+        __syncwarp();
+        const uint32_t dK = sKV + s * 2 * JT_TILE, dV = dK + JT_TILE;
+        uint32_t kb = load_tile(dK, kv_full + 8 * s, b, j, DMODEL + head * HD);
+        kb += load_tile(dV, kv_full + 8 * s, b, j, 2 * DMODEL + head * HD);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(kv_full + 8 * s, kb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_s = make_idesc(128, 128, 0);
+      constexpr uint32_t idesc_pv = make_idesc(128, HD, 1);
+      uint32_t it_kv = 0, bc = 0;
+      int pi = 0;
+      for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++pi) {
+        mbar_wait(q_full, pi & 1);
+        tc_fence_after();
+        for (int j = 0; j < n_tiles; ++j, ++it_kv, ++bc) {
+          const int s = it_kv % JT_STAGES;
+          mbar_wait(kv_full + 8 * s, (it_kv / JT_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t aK = sKV + s * 2 * JT_TILE, aV = aK + JT_TILE;
+          for (int tile = 0; tile < 2; ++tile) {
+            const uint32_t d = tmem_base + tile * 256;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16<1>(d, make_kmajor_sw128_desc(sQ + tile * JT_TILE + k * 32), make_kmajor_sw128_desc(aK + k * 32),
+                           idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(s_full + 8 * tile);
+          }
+          for (int tile = 0; tile < 2; ++tile) {
+            mbar_wait(p_full + 8 * tile, bc & 1);
+            if (j == 0 && pi > 0) mbar_wait(o_empty + 8 * tile, (pi - 1) & 1);  // previous problem's O has been read
+            tc_fence_after();
+            const uint32_t region = tmem_base + tile * 256;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_ts_bf16(region + O_COL, region + k * 8, make_mnmajor_sw128_desc(aV + k * 2048), idesc_pv,
+                           (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(kv_empty + 8 * s);      // K and V of this stage are free once these MMAs have completed
+        }
+        umma_commit(o_full);
+        umma_commit(o_full + 8);
+        umma_commit(q_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== online softmax + epilogue: one thread per query row =====
+    const int tile = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int rloc = q * 32 + lane;
+    const uint32_t treg = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tile * 256;
+    const uint32_t so_tile = sO + tile * JT_TILE;
+    const bool store_leader = q == 0 && lane == 0;
+    const float scale_log2 = 0.125f * 1.4426950408889634f;
+    const uint64_t scale2 = pk2(scale_log2, scale_log2);
+    uint32_t bc = 0;
+    int pi = 0;
+    for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++pi) {
+      int b, head, qb;
+      decode(prob, b, head, qb);
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++bc) {
+        const int valid = j == n_tiles - 1 ? p.rem + 1 : 128;   // keys of this tile that exist
+        mbar_wait(s_full + 8 * tile, bc & 1);
+        tc_fence_after();
+        // ---- pass 1: maximum of the tile ----
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        {
+          uint32_t v[32], v2[32];
+          tmem_ld_32x32(treg, v);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&cur)[32] = (c & 1) ? v2 : v;
+            uint32_t (&nxt)[32] = (c & 1) ? v : v2;
+            tmem_ld_wait();
+            if (c < 3) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
+            if (c * 32 + 32 <= valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                mx4[i & 3] = max3(mx4[i & 3], __uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(cur[i]));
+            }
+          }
+        }
+        const float m_new = fmaxf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), m);
+        // ---- rescale O and l when this row's maximum grew (warp-uniform decision: tcgen05.ld / st are warp-wide) ----
+        if (j > 0 && __any_sync(0xFFFFFFFFu, m_new > m)) {
+          const float alpha = ex2_approx((m - m_new) * scale_log2);
+          l *= alpha;
+          const uint64_t a2 = pk2(alpha, alpha);
+          uint32_t o[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld_32x32(treg + O_COL + h * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x0, x1;
+              unpk2(fma2(pk2(__uint_as_float(o[2 * i]), __uint_as_float(o[2 * i + 1])), a2, 0ull), x0, x1);
+              o[2 * i] = __float_as_uint(x0);
+              o[2 * i + 1] = __float_as_uint(x1);
+            }
+            tmem_st_32x32(treg + O_COL + h * 32, o);
+          }
+          tmem_st_wait();
+        }
+        m = m_new;
+        // ---- pass 2: p = exp2((s - m) * scale), row sum, P (bf16) over the consumed S columns ----
+        const float moff = m * scale_log2;
+        const uint64_t nmoff2 = pk2(-moff, -moff);
+        uint64_t sum2[2] = {0ull, 0ull};
+        {
+          uint32_t v[32], v2[32];
+          tmem_ld_32x32(treg, v);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&cur)[32] = (c & 1) ? v2 : v;
+            uint32_t (&nxt)[32] = (c & 1) ? v : v2;
+            tmem_ld_wait();
+            if (c < 3) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
+            float e[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a0, a1;
+              unpk2(fma2(pk2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), scale2, nmoff2), a0, a1);
+              e[2 * i] = ex2_approx(a0);
+              e[2 * i + 1] = ex2_approx(a1);
+            }
+            if (c * 32 + 32 > valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= valid) e[i] = 0.f;
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              sum2[i & 1] = add2(sum2[i & 1], pk2(e[2 * i], e[2 * i + 1]));
+              pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+            }
+            tmem_st_32x16(treg + c * 16, pk);
+          }
+        }
+        {
+          float sa, sb;
+          unpk2(add2(sum2[0], sum2[1]), sa, sb);
+          l += sa + sb;
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + 8 * tile);
+      }
+      // ---- O of this problem ----
+      mbar_wait(o_full + 8 * tile, pi & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(treg + O_COL, o0);
+      tmem_ld_32x32(treg + O_COL + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty + 8 * tile);
+      const float inv = 1.0f / l;
+      const int t_idx = 2 * qb + tile;                 // token tile of this clip
+      const int token = t_idx * 128 + rloc;
+      if (store_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      named_bar_sync(1 + tile, 128);
+      if (token < p.NT) {
+        const uint32_t dst = so_tile + rloc * 128;
+        const int sw = rloc & 7;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint32_t (&o)[32] = jj < 4 ? o0 : o1;
+          const int j8 = (jj & 3) * 8;
+          const uint32_t w0 = pack_bf16x2(__uint_as_float(o[j8]) * inv, __uint_as_float(o[j8 + 1]) * inv);
+          const uint32_t w1 = pack_bf16x2(__uint_as_float(o[j8 + 2]) * inv, __uint_as_float(o[j8 + 3]) * inv);
+          const uint32_t w2 = pack_bf16x2(__uint_as_float(o[j8 + 4]) * inv, __uint_as_float(o[j8 + 5]) * inv);
+          const uint32_t w3 = pack_bf16x2(__uint_as_float(o[j8 + 6]) * inv, __uint_as_float(o[j8 + 7]) * inv);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((jj ^ sw) << 4)), "r"(w0), "r"(w1),
+                       "r"(w2), "r"(w3) : "memory");
+        }
+      } else if (token == p.NT) {
+        __nv_bfloat16* dst = p.out + (p.cls_base + b) * p.ldo + head * HD;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint32_t (&o)[32] = jj < 4 ? o0 : o1;
+          const int j8 = (jj & 3) * 8;
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[j8]) * inv, __uint_as_float(o[j8 + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[j8 + 2]) * inv, __uint_as_float(o[j8 + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[j8 + 4]) * inv, __uint_as_float(o[j8 + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[j8 + 6]) * inv, __uint_as_float(o[j8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + jj * 8) = w;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + tile, 128);
+      if (store_leader && t_idx < n_tiles) {
+        const int row0 = b * p.NT + t_idx * 128;
+        if (t_idx < n_tiles - 1) tma_store_2d(&tmOutFull, so_tile, head * HD, row0);
+        else if (p.rem > 0) tma_store_2d(&tmOutRem, so_tile, head * HD, row0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// Returns 1 if the shape is not handled here (the caller falls back to the mma.sync streaming kernel), 0 on success.
+int launch_joint_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, int B, int NT,
+                                 long long cls_base, cudaStream_t st) {
+  if (!g_attention_impl) return 1;
+  if (NT < 1 || B < 1) return 1;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (ld % 8) || (ldo % 8)) return 1;
+  JtParams p;
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.ld = ld;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.NT = NT; p.S = NT + 1;
+  p.rem = NT % 128;
+  p.n_tiles = NT / 128 + 1;
+  p.n_qblk = (p.n_tiles + 1) / 2;
+  p.heads = 12;
+  const long long n_prob = static_cast<long long>(B) * p.heads * p.n_qblk;
+  if (n_prob > 0x7FFFFFFF || static_cast<long long>(B) * NT > 0x7FFFFFFF) return 1;
+  p.n_prob = static_cast<int>(n_prob);
+  p.cls_base = cls_base;
+  const size_t smem = 1024 + (2 + 2 * JT_STAGES + 2) * static_cast<size_t>(JT_TILE) + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(joint_attention_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error("attention(joint sm100) attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const uint64_t rows = static_cast<uint64_t>(B) * NT;   // patch rows: the boxes never read the CLS rows behind them
+  CUtensorMap tmFull, tmRem, tmOutFull, tmOutRem;
+  if (int rc = make_tmap_bf16_2d(&tmFull, qkv, rows, 3 * DMODEL, ld, 128, HD)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmRem, qkv, rows, 3 * DMODEL, ld, p.rem > 0 ? p.rem : 1, HD)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmOutFull, out, rows, DMODEL, ldo, 128, HD)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmOutRem, out, rows, DMODEL, ldo, p.rem > 0 ? p.rem : 1, HD)) return rc;
+  const int grid = p.n_prob < num_sms() ? p.n_prob : num_sms();
+  joint_attention_sm100_kernel<<<grid, NUM_THREADS, smem, st>>>(tmFull, tmRem, tmOutFull, tmOutRem, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : set_error("attention(joint sm100) launch: %s", cudaGetErrorString(e));
+}
+
 }  // namespace dvst

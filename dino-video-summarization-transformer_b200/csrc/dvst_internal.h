@@ -100,6 +100,9 @@ int launch_attention_probs(const void* qkv, long long ld, float* probs, int B, i
 int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode,
                                    int B, int T, int N, long long cls_base, cudaStream_t st, void* scratch = nullptr,
                                    long long scratch_bytes = 0);
+// flash-style tcgen05 kernel for joint space-time attention (mode 2, bf16): NT = patch tokens per clip; same return codes
+int launch_joint_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, int B, int NT,
+                                 long long cls_base, cudaStream_t st);
 void set_attention_impl(int impl);  // 1 (default) tcgen05 (+ one-pass softmax with scratch), 2 tcgen05 two-pass, 0 mma.sync
 
 int launch_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int V, int rate,
