@@ -621,13 +621,18 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
 // The tokens of a clip are contiguous rows (patch tokens b*NT .. b*NT + NT - 1) plus the clip's CLS row, kept as the LAST
 // token (attention does not depend on the key order): every tile is one 2-D TMA box, except the last one, which is a
 // shorter box (NT % 128 rows) plus a 128-byte copy of the CLS row; its padding keys are masked.
-// tcgen05.mma instructions of one thread execute in order, so "S of the next key tile complete" (what the softmax warps
-// wait for) implies "P V of the previous tile complete": the O rescale needs no barrier of its own.
+// S of the next key tile is issued BEFORE P V of the current one (P has its own TMEM columns), so the softmax warps wait
+// for one MMA round trip per key tile; "P V complete" is its own barrier, waited before P is overwritten / O is rescaled.
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
 constexpr int JT_STAGES = 4;
 constexpr int JT_TILE = 128 * 128;  // bytes of one 128-row x 64-column bf16 tile
+// TMEM columns of one Q tile's 256-column region: S fp32 [0, 128), P bf16 [128, 192), O fp32 [192, 256).  P has its own
+// columns so that S of the NEXT key tile can be issued before P V of the current one: the softmax warps then wait for one
+// MMA round trip per key tile instead of two.
+constexpr int JT_P_COL = 128;
+constexpr int JT_O_COL = 192;
 
 struct JtParams {
   const __nv_bfloat16* qkv;
@@ -652,6 +657,23 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
         "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+        "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+        "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+        "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+        "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
@@ -675,7 +697,7 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
   const uint32_t kv_empty = kv_full + 8 * JT_STAGES;          // [JT_STAGES]
   const uint32_t s_full = kv_empty + 8 * JT_STAGES;           // [2]
   const uint32_t p_full = s_full + 16;                        // [2]
-  const uint32_t o_full = p_full + 16;                        // [2]
+  const uint32_t o_full = p_full + 16;                        // [2]  P V of a key tile complete (one phase per key tile)
   const uint32_t o_empty = o_full + 16;                       // [2]
   const uint32_t tmem_slot = o_empty + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
@@ -771,39 +793,72 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
       // ===== MMA issuer =====
       constexpr uint32_t idesc_s = make_idesc(128, 128, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, HD, 1);
-      uint32_t it_kv = 0, bc = 0;
+      // The two Q tiles run decoupled: whenever a tile's P of key tile j is ready, its P V (j) and right behind it its
+      // S (j + 1) are issued - so while one tile sits in the softmax (MUFU bound) the tensor pipe serves the other one,
+      // and the max pass of a tile (TMEM latency bound) hides behind the other tile's exponentials.
+      uint32_t kv_base = 0;   // key-tile iterations issued by the producer before this problem
+      uint32_t bcs = 0;       // blocks completed per tile before this problem (parity of s_full / p_full)
       int pi = 0;
+      auto issue_s = [&](int tile, uint32_t it) {
+        const int s = it % JT_STAGES;
+        tc_fence_after();
+        const uint32_t aK = sKV + s * 2 * JT_TILE;
+        const uint32_t d = tmem_base + tile * 256;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16<1>(d, make_kmajor_sw128_desc(sQ + tile * JT_TILE + k * 32), make_kmajor_sw128_desc(aK + k * 32),
+                       idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(s_full + 8 * tile);
+      };
       for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++pi) {
         mbar_wait(q_full, pi & 1);
         tc_fence_after();
-        for (int j = 0; j < n_tiles; ++j, ++it_kv, ++bc) {
-          const int s = it_kv % JT_STAGES;
-          mbar_wait(kv_full + 8 * s, (it_kv / JT_STAGES) & 1);
-          tc_fence_after();
-          const uint32_t aK = sKV + s * 2 * JT_TILE, aV = aK + JT_TILE;
-          for (int tile = 0; tile < 2; ++tile) {
-            const uint32_t d = tmem_base + tile * 256;
+        int jt[2] = {0, 0};                 // current key tile per Q tile
+        bool need_s[2] = {true, true};      // true: S (jt) not issued yet; false: waiting for P (jt)
+        // every wait in this loop is a poll: a blocking wait for one tile (e.g. for a K / V stage that the OTHER tile has
+        // not released yet) would stop this thread from serving the other tile and deadlock the pair
+        while (jt[0] < n_tiles || jt[1] < n_tiles) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16<1>(d, make_kmajor_sw128_desc(sQ + tile * JT_TILE + k * 32), make_kmajor_sw128_desc(aK + k * 32),
-                           idesc_s, k != 0 ? 1u : 0u);
-            umma_commit(s_full + 8 * tile);
-          }
           for (int tile = 0; tile < 2; ++tile) {
-            mbar_wait(p_full + 8 * tile, bc & 1);
-            if (j == 0 && pi > 0) mbar_wait(o_empty + 8 * tile, (pi - 1) & 1);  // previous problem's O has been read
+            const int j = jt[tile];
+            if (j >= n_tiles) continue;
+            const uint32_t it = kv_base + j;
+            const int s = it % JT_STAGES;
+            if (need_s[tile]) {
+              if (!mbar_try_wait(kv_full + 8 * s, (it / JT_STAGES) & 1)) continue;
+              issue_s(tile, it);
+              need_s[tile] = false;
+              continue;
+            }
+            if (!mbar_try_wait(p_full + 8 * tile, (bcs + j) & 1)) continue;
+            // (the softmax warps release O of the previous problem on their own: this wait cannot involve the other tile)
+            if (j == 0 && pi > 0) mbar_wait(o_empty + 8 * tile, (pi - 1) & 1);
             tc_fence_after();
+            // S of the next key tile first (the softmax warps have finished reading S of this one), if its K is there
+            bool next_s_issued = false;
+            if (j + 1 < n_tiles) {
+              const uint32_t itn = it + 1;
+              if (mbar_try_wait(kv_full + 8 * (itn % JT_STAGES), (itn / JT_STAGES) & 1)) {
+                issue_s(tile, itn);
+                next_s_issued = true;
+              }
+            }
+            const uint32_t aV = sKV + s * 2 * JT_TILE + JT_TILE;
             const uint32_t region = tmem_base + tile * 256;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_ts_bf16(region + O_COL, region + k * 8, make_mnmajor_sw128_desc(aV + k * 2048), idesc_pv,
+              umma_ts_bf16(region + JT_O_COL, region + JT_P_COL + k * 8, make_mnmajor_sw128_desc(aV + k * 2048), idesc_pv,
                            (j | k) != 0 ? 1u : 0u);
+            umma_commit(o_full + 8 * tile);
+            // the stage is free once BOTH tiles' MMAs on it have completed: the later of the two commits it
+            if (jt[tile ^ 1] > j) umma_commit(kv_empty + 8 * s);
+            jt[tile] = j + 1;
+            need_s[tile] = !next_s_issued;
           }
-          umma_commit(kv_empty + 8 * s);      // K and V of this stage are free once these MMAs have completed
         }
-        umma_commit(o_full);
-        umma_commit(o_full + 8);
         umma_commit(q_empty);
+        kv_base += n_tiles;
+        bcs += n_tiles;
       }
     }
   } else if (warp >= 4) {
@@ -826,38 +881,41 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
         const int valid = j == n_tiles - 1 ? p.rem + 1 : 128;   // keys of this tile that exist
         mbar_wait(s_full + 8 * tile, bc & 1);
         tc_fence_after();
-        // ---- pass 1: maximum of the tile ----
+        // ---- pass 1: maximum of the tile (two 64-column TMEM loads: the pass is latency bound) ----
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        {
-          uint32_t v[32], v2[32];
-          tmem_ld_32x32(treg, v);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t (&cur)[32] = (c & 1) ? v2 : v;
-            uint32_t (&nxt)[32] = (c & 1) ? v : v2;
-            tmem_ld_wait();
-            if (c < 3) tmem_ld_32x32(treg + (c + 1) * 32, nxt);
-            if (c * 32 + 32 <= valid) {
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[64];
+          tmem_ld_32x64(treg + h * 64, v);
+          tmem_ld_wait();
+          if (h * 64 + 64 <= valid) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                mx4[i & 3] = max3(mx4[i & 3], __uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
-            } else {
+            for (int i = 0; i < 32; ++i)
+              mx4[i & 3] = max3(mx4[i & 3], __uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(cur[i]));
-            }
+            for (int i = 0; i < 64; ++i)
+              if (h * 64 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
           }
         }
-        const float m_new = fmaxf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), m);
-        // ---- rescale O and l when this row's maximum grew (warp-uniform decision: tcgen05.ld / st are warp-wide) ----
-        if (j > 0 && __any_sync(0xFFFFFFFFu, m_new > m)) {
-          const float alpha = ex2_approx((m - m_new) * scale_log2);
+        const float bmax = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // ---- lazy reference: m only moves when a row's maximum exceeds it by more than 2^8 (44 raw score units), so the
+        // probabilities stay <= 256 and the O / l rescale (tcgen05.ld + st of 64 columns, decided per warp) becomes rare
+        // after the first key tiles instead of running whenever any of a warp's 32 rows sees a new maximum ----
+        const bool grow = j == 0 || bmax > m + 44.0f;
+        // P V of the previous key tile must have completed before its P columns are overwritten and before O is touched
+        if (j > 0) {
+          mbar_wait(o_full + 8 * tile, (bc - 1) & 1);
+          tc_fence_after();
+        }
+        if (j > 0 && __any_sync(0xFFFFFFFFu, grow)) {
+          const float alpha = grow ? ex2_approx((m - bmax) * scale_log2) : 1.0f;
           l *= alpha;
           const uint64_t a2 = pk2(alpha, alpha);
           uint32_t o[32];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            tmem_ld_32x32(treg + O_COL + h * 32, o);
+            tmem_ld_32x32(treg + JT_O_COL + h * 32, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -866,11 +924,11 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
               o[2 * i] = __float_as_uint(x0);
               o[2 * i + 1] = __float_as_uint(x1);
             }
-            tmem_st_32x32(treg + O_COL + h * 32, o);
+            tmem_st_32x32(treg + JT_O_COL + h * 32, o);
           }
           tmem_st_wait();
         }
-        m = m_new;
+        if (grow) m = bmax;
         // ---- pass 2: p = exp2((s - m) * scale), row sum, P (bf16) over the consumed S columns ----
         const float moff = m * scale_log2;
         const uint64_t nmoff2 = pk2(-moff, -moff);
@@ -903,7 +961,7 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
               sum2[i & 1] = add2(sum2[i & 1], pk2(e[2 * i], e[2 * i + 1]));
               pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
             }
-            tmem_st_32x16(treg + c * 16, pk);
+            tmem_st_32x16(treg + JT_P_COL + c * 16, pk);
           }
         }
         {
@@ -916,12 +974,12 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full + 8 * tile);
       }
-      // ---- O of this problem ----
-      mbar_wait(o_full + 8 * tile, pi & 1);
+      // ---- O of this problem (P V of the last key tile complete) ----
+      mbar_wait(o_full + 8 * tile, (bc - 1) & 1);
       tc_fence_after();
       uint32_t o0[32], o1[32];
-      tmem_ld_32x32(treg + O_COL, o0);
-      tmem_ld_32x32(treg + O_COL + 32, o1);
+      tmem_ld_32x32(treg + JT_O_COL, o0);
+      tmem_ld_32x32(treg + JT_O_COL + 32, o1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
