@@ -98,7 +98,8 @@ def _attn_ref(q, k, v):
 
 @pytest.mark.parametrize("mode,B,T,N", [(0, 2, 16, 9), (0, 1, 3, 5), (0, 1, 30, 4), (0, 1, 60, 2), (0, 1, 1, 3),
                                         (1, 2, 3, 196), (1, 1, 2, 36), (2, 2, 2, 196), (3, 2, 2, 196),
-                                        (2, 1, 5, 196), (2, 1, 32, 196)])
+                                        (2, 1, 5, 196), (2, 1, 32, 196), (2, 3, 3, 196), (2, 2, 1, 36), (2, 1, 2, 64),
+                                        (2, 5, 1, 196)])
 def test_attention_modes(dev, mode, B, T, N):
     torch.manual_seed(mode * 100 + T)
     L = _lib.lib()
@@ -458,3 +459,33 @@ def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
     _lib.check(L.dvst_attention(_lib.ptr(qkv), 2304, _lib.ptr(out2), 768, _lib.ptr(cls2), mode, B, T, N, Mt,
                                 _lib.cur_stream()))
     assert _rel(out.float(), out2.float()) < 5e-3
+
+
+def test_joint_attention_rescale_path(dev):
+    """Joint (flash-style tcgen05) attention with scores that keep growing along the keys, by far more than the lazy
+    reference's 2^8 slack per key tile: the O / l rescale runs on (almost) every key tile and must stay exact; a second
+    half of the queries sees decreasing scores (no rescale after the first tile)."""
+    torch.manual_seed(11)
+    L = _lib.lib()
+    B, T, N = 2, 4, 196
+    NT = N * T
+    Mt = B * NT
+    qkv = (torch.randn(Mt + B, 2304, device=dev) * 1.0).bfloat16()
+    u = torch.nn.functional.normalize(torch.randn(64, device=dev), dim=0)
+    tok = torch.arange(NT, device=dev).repeat(B).float()
+    ramp = (tok / 128.0).floor()                               # key tile index
+    for h in range(12):
+        qkv[:Mt, 768 + h * 64: 768 + (h + 1) * 64] += (ramp[:, None] * 9.0 * u[None, :]).bfloat16()
+        qkv[0:Mt:2, h * 64: (h + 1) * 64] += (10.0 * u).bfloat16()      # even queries: scores grow ~90 per key tile
+        qkv[1:Mt:2, h * 64: (h + 1) * 64] -= (10.0 * u).bfloat16()      # odd queries: scores fall
+    out = torch.zeros(Mt + B, 768, device=dev, dtype=torch.bfloat16)
+    cls_out = torch.zeros(B, T, 768, device=dev)
+    _lib.check(L.dvst_attention(_lib.ptr(qkv), 2304, _lib.ptr(out), 768, _lib.ptr(cls_out), 2, B, T, N, Mt,
+                                _lib.cur_stream()))
+    q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
+    ref = torch.zeros(Mt + B, 768, device=dev)
+    for bb in range(B):
+        r = torch.cat([torch.tensor([Mt + bb], device=dev), torch.arange(bb * NT, (bb + 1) * NT, device=dev)])
+        ref[r] = _attn_ref(q[r], k[r], v[r])
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out.float(), ref) < 5e-3
