@@ -146,6 +146,24 @@ def window_starts(F, local_clip_size=3, global_clip_size=30):
     return G, ls, gs
 
 
+def short_video_clips(F, local_clip_size=3):
+    """(student frame indices, teacher frame indices) for a video with F < local_clip_size sampled frames.  The reference
+    does not treat it as malformed: get_views_of_video_same_size clamps G = F, its local slice frames[F-local : F] has a
+    negative start (python wrap-around -> max(2F - local, 0)) and is written into the zero [3,G,H,W] tensor by broadcast
+    (dino_loss_loader.py:126-161), so with local = 3 a 2-frame video is scored on student [f1, f1] vs teacher [f0, f1]
+    and a 1-frame video on [f0] vs [f0]; every frame gets that same pair.  Slices the reference cannot broadcast raise."""
+    start = max(2 * F - local_clip_size, 0)
+    n = F - start
+    if n == 1:
+        s_idx = [start] * F
+    elif n == F:
+        s_idx = list(range(F))
+    else:
+        raise ValueError(f"the reference cannot build views for {F} frames with local_clip_size {local_clip_size} "
+                         f"(broadcast of {n} frames into {F})")
+    return s_idx, list(range(F))
+
+
 class HeadScorer:
     """Mode-H loss: DINOHead bottleneck + fused last layer / softmax / cross-entropy (never materialises logits)."""
 
@@ -193,7 +211,7 @@ def _forward_windows(model, frames, starts, T, max_clips):
 
 
 def _dummy_losses(model, dev, dino_loss, scorer, local_clip_size, global_clip_size):
-    """Malformed video -> the reference's dummy views: `global_clip_size` identical losses of the all-zero
+    """Malformed video (frames that are not 224 x 224 after the crop) -> the reference's dummy views: `global_clip_size` identical losses of the all-zero
     (T=local, T=60) pair (dino_loss_loader.py:36-38,103-107; dino_similarity.py:78)."""
     zs = torch.zeros(local_clip_size, 3, 224, 224, device=dev)
     zt = torch.zeros(60, 3, 224, 224, device=dev)
@@ -229,13 +247,23 @@ def score_videos_device(model, videos, dino_loss, local_clip_size=3, global_clip
             raise ValueError("all videos of a batch must live on the same device")
     out = [None] * len(videos)
     with torch.cuda.device(dev):
-        good = [i for i, v in enumerate(videos)
-                if v.dim() == 4 and v.shape[0] >= local_clip_size and v.shape[2] == 224 and v.shape[3] == 224]
-        if len(good) < len(videos):
+        ok_shape = [v.dim() == 4 and v.shape[0] >= 1 and v.shape[2] == 224 and v.shape[3] == 224 for v in videos]
+        good = [i for i, v in enumerate(videos) if ok_shape[i] and v.shape[0] >= local_clip_size]
+        short = [i for i, v in enumerate(videos) if ok_shape[i] and v.shape[0] < local_clip_size]
+        if len(good) + len(short) < len(videos):
             dummy = _dummy_losses(model, dev, dino_loss, scorer, local_clip_size, global_clip_size)
             for i in range(len(videos)):
-                if i not in good:
+                if not ok_shape[i]:
                     out[i] = dummy
+        for i in short:
+            # fewer frames than the local window: the reference's broadcast views (short_video_clips), F equal losses
+            v = videos[i].detach().to(torch.float32)
+            F = v.shape[0]
+            si, ti = short_video_clips(F, local_clip_size)
+            fs = _forward_windows(model, v[si].contiguous(), [0], F, 1)
+            ft = _forward_windows(model, v[ti].contiguous(), [0], F, 1)
+            idx = torch.zeros(F, dtype=torch.int32, device=dev)
+            out[i] = scorer.pair_losses(fs, ft, idx, idx) if scorer is not None else dino_loss.pair_losses(fs, ft, idx, idx)
         if not good:
             return out
         clips = [videos[i].detach().to(torch.float32).contiguous() for i in good]

@@ -10,7 +10,7 @@ def video_cost(F, local_clip_size=3, global_clip_size=30):
     """Relative cost of scoring a video with F sampled frames: distinct student windows x T=local + distinct teacher
     windows x T=G (FLOPs are ~linear in T)."""
     if F < local_clip_size:
-        return local_clip_size + 60
+        return 2 * max(F, 1)   # one student + one teacher clip of F frames (dino_similarity.short_video_clips)
     G = min(global_clip_size, F)
     return (F - local_clip_size + 1) * local_clip_size + (F - G + 1) * G
 
@@ -40,7 +40,7 @@ def gather_scores(local_scores, lengths, parts, device):
         return {i: local_scores[i].tolist() for i in parts[0]}
 
     def width(F):
-        return max(F, 30)  # dummy videos produce 30 values
+        return max(F, 30)  # dummy (wrong-crop) videos produce 30 values
     n_max = max(len(p) for p in parts)
     f_max = max(width(f) for f in lengths) if lengths else 1
     buf = torch.zeros(n_max, f_max, dtype=torch.float32, device=device)

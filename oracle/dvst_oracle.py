@@ -262,15 +262,36 @@ def window_starts(F, local_size=3, global_size=30):
     return G, out
 
 
+def short_video_clips(F, local_size=3):
+    """Frame indices of the (student, teacher) clips every frame of a video with F < local_size sampled frames is scored
+    on (dino_loss_loader.py:126-171 with len(frames) < local_size, then dino_similarity.py:78): G = F; the local slice
+    frames[F - local_size : F] starts at a negative index, i.e. at max(2F - local_size, 0); its n frames are written into
+    the zero [3, G, H, W] tensor through `tensor_padded[:, :local_size] = tensor_local`, which broadcasts n = 1 to all G
+    frames, fits n = G exactly, and raises for anything else (as the reference does).  The teacher clip is frames[0:F]."""
+    start = max(2 * F - local_size, 0)
+    n = F - start
+    if n == 1:
+        s_idx = [start] * F
+    elif n == F:
+        s_idx = list(range(F))
+    else:
+        raise ValueError(f"the reference cannot build views for {F} frames with local_clip_size {local_size} "
+                         f"(broadcast of {n} frames into {F})")
+    return s_idx, list(range(F))
+
+
 def score_video(sd, frames, local_size=3, global_size=30, teacher_temp=0.02, student_temp=0.3, head=None,
                 center=None, attention_type="divided_space_time", batch=8):
     """dino_similarity() inner loop - dino_similarity.py:66-93 (mode R when head is None; mode H = DINOHead on both
     features first).  frames [F,3,H,W] (already normalised / cropped).  Returns a python list of F floats.
-    Malformed videos (F < local_size, or crop != 224) follow the dummy path (dino_loss_loader.py:36-38,103-107):
-    `global_size` losses of the all-zero (T=local_size, T=60) pair."""
+    Wrong crops follow the dummy path (dino_loss_loader.py:36-38,103-107): `global_size` losses of the all-zero
+    (T=local_size, T=60) pair.  Videos shorter than the local window (F < local_size) are NOT dummies in the reference:
+    get_views_of_video_same_size clamps G = F, its local slice frames[F-local_size:F] has a negative start (python
+    wrap-around), and the zero-padded [3,G,H,W] tensor receives it by broadcast (dino_loss_loader.py:147-161), so the
+    student sees T = F frames; every frame of the video gets that same pair (short_video_clips)."""
     F = frames.shape[0]
     dt = sd["pos_embed"].dtype
-    if F < local_size or frames.shape[-1] != 224 or frames.shape[-2] != 224:
+    if frames.shape[-1] != 224 or frames.shape[-2] != 224 or F == 0:
         zs = torch.zeros(1, 3, local_size, 224, 224, dtype=dt)
         zt = torch.zeros(1, 3, 60, 224, 224, dtype=dt)
         fs, ft = forward_features(sd, zs, attention_type), forward_features(sd, zt, attention_type)
@@ -278,6 +299,14 @@ def score_video(sd, frames, local_size=3, global_size=30, teacher_temp=0.02, stu
             fs, ft = dino_head(head, fs), dino_head(head, ft)
         c = torch.zeros_like(fs) if center is None else center
         return [float(dino_pair_loss(fs, ft, c, teacher_temp, student_temp)[0])] * global_size
+    if F < local_size:
+        s_idx, t_idx = short_video_clips(F, local_size)
+        fs = forward_features(sd, frames[s_idx].permute(1, 0, 2, 3)[None].to(dt), attention_type)
+        ft = forward_features(sd, frames[t_idx].permute(1, 0, 2, 3)[None].to(dt), attention_type)
+        if head is not None:
+            fs, ft = dino_head(head, fs), dino_head(head, ft)
+        c = torch.zeros_like(fs) if center is None else center
+        return [float(dino_pair_loss(fs, ft, c, teacher_temp, student_temp)[0])] * F
     G, starts = window_starts(F, local_size, global_size)
     cache = {}
 

@@ -53,10 +53,21 @@ BACKBONE_CASES = [
 ]
 
 
-def gen_backbone():
+# Round 2: the benchmark's own shapes at full depth (cfg2: T = 16; cfg3's teacher window: T = 30; cfg5: T = 32 divided at
+# depth 12 and joint space-time at depth 2 - 6 273 tokens, 49 key tiles of the flash-style kernel).  Kept in their own
+# file so that the round-1 fixtures stay byte-identical.
+BACKBONE_CASES_R2 = [
+    ("cfg2_full_T16", 0, 12, 8, "divided_space_time", 120, 2, 16, 224),
+    ("cfg3_full_T30", 0, 12, 8, "divided_space_time", 121, 1, 30, 224),
+    ("cfg5_full_T32", 0, 12, 8, "divided_space_time", 122, 1, 32, 224),
+    ("cfg5_d2_joint_T32", 2, 2, 8, "joint_space_time", 123, 1, 32, 224),
+]
+
+
+def gen_backbone(cases=None, fname="backbone.pt"):
     out = {}
     cache = {}
-    for (name, sw, depth, T0, att, sx, B, T, crop) in BACKBONE_CASES:
+    for (name, sw, depth, T0, att, sx, B, T, crop) in (cases or BACKBONE_CASES):
         key = (sw, depth, T0, att)
         if key not in cache:
             sd = synth_backbone_state_dict(sw, depth=depth, num_frames=T0, attention_type=att)
@@ -68,7 +79,7 @@ def gen_backbone():
         out[name] = dict(seed_w=sw, depth=depth, num_frames=T0, attention_type=att, seed_x=sx, B=B, T=T, crop=crop,
                          feat=feat.clone())
         print("backbone", name, tuple(feat.shape), float(feat.std()))
-    torch.save(out, os.path.join(GOLD, "backbone.pt"))
+    torch.save(out, os.path.join(GOLD, fname))
     return cache
 
 
@@ -138,6 +149,18 @@ def gen_windows():
         out[str(F)] = dict(G=G, starts=starts)
     json.dump(out, open(os.path.join(GOLD, "windows.json"), "w"))
     print("windows", len(out))
+    # videos shorter than the local window (F = 1, 2): the loader's broadcast views + the driver's `[:, :, :3]` slice
+    short = {}
+    for F in (1, 2):
+        frames = torch.arange(F, dtype=torch.float32).reshape(F, 1, 1, 1).expand(F, 3, 1, 1).contiguous()
+        views = gv(frames, 3, 30)                       # [2F, 3, G, 1, 1]
+        pairs = []
+        for i in range(F):
+            loc = views[2 * i][:, :3]                   # dino_similarity.py:78
+            pairs.append(dict(student=[int(v) for v in loc[0, :, 0, 0]], teacher=[int(v) for v in views[2 * i + 1][0, :, 0, 0]]))
+        short[str(F)] = pairs
+    json.dump(short, open(os.path.join(GOLD, "windows_short.json"), "w"))
+    print("windows_short", short)
 
 
 def gen_selection():
@@ -252,6 +275,17 @@ def gen_knn():
     json.dump(out, open(os.path.join(GOLD, "knn.json"), "w"))
 
 
+def gen_lengths():
+    """Histogram of the per-video loss-list lengths (= sampled frames F) of the shipped MSVD loss file: the "MSVD-shaped"
+    length distribution bench.py's cfg3 leg draws its synthetic videos from."""
+    import collections
+    shipped = json.load(open(os.path.join(ref_shim.REF_ROOT, "loss_values", "loss_msvd_4_3_30.json")))
+    hist = collections.Counter(len(v) for v in shipped.values())
+    json.dump({"source": "loss_values/loss_msvd_4_3_30.json: len(list) per video", "videos": len(shipped),
+               "hist": {str(k): hist[k] for k in sorted(hist)}}, open(os.path.join(GOLD, "msvd_lengths.json"), "w"))
+    print("lengths", len(shipped), "videos,", len(hist), "distinct lengths")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["backbone", "head", "windows", "selection", "driver", "attn", "knn"]
     models = gen_backbone() if ("backbone" in what or "head" in what) else None
@@ -267,3 +301,7 @@ if __name__ == "__main__":
         gen_attn()
     if "knn" in what:
         gen_knn()
+    if "lengths" in what:
+        gen_lengths()
+    if "backbone_r2" in what:
+        gen_backbone(BACKBONE_CASES_R2, "backbone_r2.pt")

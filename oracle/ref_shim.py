@@ -11,7 +11,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DVST_REFERENCE_ROOT", "/root/reference")
+# Where the reference lives: the mounted tree in the authoring container; on the GPU box (no /root/reference) the
+# git-ignored copy `oracle/_ref/` that `oracle/stage_reference.py` (run by __graft_entry__.build() here) stages so that
+# bench.py's reference arm can time the UNMODIFIED reference modules on the box's host cores.
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref")
+
+
+def _default_root():
+    if os.path.isfile(os.path.join("/root/reference", "models", "timesformer.py")):
+        return "/root/reference"
+    return _STAGED
+
+
+REF_ROOT = os.environ.get("DVST_REFERENCE_ROOT") or _default_root()
 
 
 def available():

@@ -54,6 +54,10 @@ def _relmax(a, b):
 
 
 GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "backbone.pt"))
+# round 2: the benchmark's own shapes at full depth, produced by the unmodified reference (oracle/make_golden.py):
+# cfg2 (depth 12, T = 16), cfg3's teacher window (depth 12, T = 30), cfg5 (depth 12 divided T = 32; joint T = 32 with
+# 6 273 tokens = 49 key tiles of the flash-style kernel)
+GOLD.update(torch.load(os.path.join(os.path.dirname(__file__), "golden", "backbone_r2.pt")))
 
 
 @pytest.mark.parametrize("name", sorted(GOLD))
@@ -438,3 +442,19 @@ def test_forward_is_cuda_graph_capturable(dev):
         g.replay()
         torch.cuda.synchronize()
     assert torch.equal(out, ref2)
+
+
+def test_nccl_world2_extract_features_update_center_gather_scores(dev):
+    """The path's three collectives under NCCL with the real model on two GPUs (tools/nccl_check.py): extract_features'
+    all-gathers (eval_knn.py:111-132), the training loss' center all-reduce (train_ssl.py:673-691) and the gather of
+    per-video score vectors, each compared with the single-GPU result.  Skipped on a one-GPU box (the driver's GPU tier);
+    run with `gpurun --gpus 2`."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541",
+                          os.path.join(root, "tools", "nccl_check.py")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "nccl ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

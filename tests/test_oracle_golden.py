@@ -13,11 +13,13 @@ from dvst_b200.testing import synth_backbone_state_dict, synth_clips, synth_head
 
 @pytest.fixture(scope="module")
 def backbone_gold(golden_dir):
-    return torch.load(os.path.join(golden_dir, "backbone.pt"))
+    g = torch.load(os.path.join(golden_dir, "backbone.pt"))
+    g.update(torch.load(os.path.join(golden_dir, "backbone_r2.pt")))
+    return g
 
 
 @pytest.mark.parametrize("name", ["cfg1_full_T8", "d2_T5", "d2_T30", "d2_T16", "d2_T4_crop96", "d2_T1", "d2_joint_T4",
-                                  "d2_space_T4"])
+                                  "d2_space_T4", "cfg2_full_T16", "cfg5_d2_joint_T32"])
 def test_backbone_matches_reference(backbone_gold, name):
     c = backbone_gold[name]
     sd = synth_backbone_state_dict(c["seed_w"], depth=c["depth"], num_frames=c["num_frames"],
