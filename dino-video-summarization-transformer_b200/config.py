@@ -121,7 +121,11 @@ class DecodedVideoDataset:
 
     def __getitem__(self, index):
         import torchvision.io as io
-        video, _, _ = io.read_video(self._path_to_videos[index], pts_unit='sec')
+        read_video = getattr(io, "read_video", None)
+        if read_video is None:
+            raise RuntimeError("this torchvision has no io.read_video (the decoder the reference uses, "
+                               "dino_loss_loader.py:81): pass `dataset=` an iterable of (decoded uint8 frames, path)")
+        video, _, _ = read_video(self._path_to_videos[index], pts_unit='sec')
         return video, self._path_to_videos[index]
 
     def __iter__(self):

@@ -202,6 +202,7 @@ int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw
   g.act = act;
   if (x_inout != nullptr) {
     if (ln_stats != nullptr) return set_error("dvst_gemm_bf16_ln: choose the consumer (ln_stats) or the producer (x_inout) form");
+    if (N != 768) return set_error("dvst_gemm_bf16_ln: the producer form is defined for N = 768 (6 statistic blocks per row), got %d", N);
     g.residual = x_inout; g.ldr = ldx; g.out = x_inout; g.ldo = ldx; g.out_kind = 3;
     g.xb = xb; g.ldxb = ldxb; g.stats_out = stats_out;
   } else {

@@ -665,7 +665,8 @@ int launch_attention_probs(const void* qkv, long long ld, float* probs, int B, i
   if (p.n_seq <= 0) return 0;
   if (p.S > 256) return set_error("attention map: %d tokens per frame exceed the supported 256", p.S);
   const size_t smem = (static_cast<size_t>(p.S) * 65 + 8 * 64) * sizeof(float);
-  static size_t cur = 0;
+  static PerDevice<size_t> cur_cache;
+  size_t& cur = cur_cache.get();
   if (smem > cur) {
     cudaError_t ee = cudaFuncSetAttribute(attention_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem));
@@ -734,7 +735,10 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
     kern<<<static_cast<unsigned>((n_prob + ppc - 1) / ppc), 128, smem, st>>>(p);
     return 0;
   };
-  static size_t cur_t = 0, cur1 = 0, cur1s = 0, cur4 = 0, cur4s = 0;
+  struct Cur { size_t t, k1, k1s, k4, k4s; };
+  static PerDevice<Cur> cur_cache;
+  Cur& cc = cur_cache.get();
+  size_t &cur_t = cc.t, &cur1 = cc.k1, &cur1s = cc.k1s, &cur4 = cc.k4, &cur4s = cc.k4s;
   const size_t per = static_cast<size_t>(S_pad) * 128;
   int rc = 0;
   if (!split && (mode == 1 || mode == 3)) {
@@ -768,7 +772,8 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
     dim3 grid(static_cast<unsigned>((p.S + 63) / 64), static_cast<unsigned>(n_prob));
     if (n_prob > 65535) return set_error("attention: too many (sequence, head) problems for the streaming kernel");
     if (split) {
-      static bool set = false;
+      static PerDevice<bool> set_cache;
+      bool& set = set_cache.get();
       if (!set) { cudaFuncSetAttribute(attention_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4 * 64 * 128); set = true; }
       attention_stream_kernel<true><<<grid, 128, 2 * 4 * 64 * 128, st>>>(p);
     } else {

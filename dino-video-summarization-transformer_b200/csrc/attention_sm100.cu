@@ -569,7 +569,8 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
   const int n_tiles = S > 128 ? 2 : 1;
   const size_t kv_bytes = (static_cast<size_t>(p.NPAD) * 128 + 1023) & ~static_cast<size_t>(1023);
   const size_t smem = 1024 + 2 * (n_tiles * TILE_BYTES + 2 * kv_bytes) + n_tiles * TILE_BYTES + 128;
-  static size_t cur = 0;
+  static PerDevice<size_t> cur_cache;
+  size_t& cur = cur_cache.get();
   if (smem > cur) {
     cudaError_t e = cudaFuncSetAttribute(spatial_attention_sm100_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1060,7 +1061,8 @@ int launch_joint_attention_sm100(const void* qkv, long long ld, void* out, long 
   p.n_prob = static_cast<int>(n_prob);
   p.cls_base = cls_base;
   const size_t smem = 1024 + (2 + 2 * JT_STAGES + 2) * static_cast<size_t>(JT_TILE) + 256;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_cache;
+  bool& attr_set = attr_cache.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(joint_attention_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));

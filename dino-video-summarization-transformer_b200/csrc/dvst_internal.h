@@ -11,7 +11,15 @@ namespace dvst {
 int set_error(const char* fmt, ...);
 // Every kernel launch made by the library bumps this counter (read through dvst_launch_count()).
 void count_launch();
-int num_sms();
+int num_sms();   // of the CURRENT device
+// Per-device caches (kernel attributes such as the dynamic shared-memory opt-in are per device, and so is the SM count):
+// indexed by cudaGetDevice(), so a process that drives several GPUs (or moves a model to another device) stays correct.
+constexpr int kMaxDevices = 64;
+int device_slot();
+template <class T> struct PerDevice {
+  T v[kMaxDevices] = {};
+  T& get() { return v[device_slot()]; }
+};
 
 // Optional live per-kernel timing (CUDA events on the launching stream), used by bench.py for the roofline figures.
 // PROF_GEMM_HBM: short-K (K <= 1024) deferred-LayerNorm producer GEMMs - bounded by their residual / output streams (work is
@@ -81,6 +89,10 @@ int launch_pair_loss(const float* s, long long lds, const float* t, long long ld
 int launch_embed_table(const float* pos, int P, const float* time_embed, int T0, float* out, int gh, int gw, int T,
                        cudaStream_t st);
 // mode: 0 temporal, 1 spatial (shared CLS per clip), 2 joint, 3 space-only (one CLS row per (b, t))
+// Kernel choice (all sm_100a device kernels - there is no host / library fallback): bf16 modes 1 / 3 with <= 256 tokens per
+// frame and mode 2 run on the tcgen05 kernels of attention_sm100.cu; shapes those do not cover (more than 256 tokens per
+// frame, rows not 16-byte aligned), the temporal sequences and split precision run on the mma.sync kernels of attention.cu.
+// The dispatch depends on the shape only, never on the batch size.
 // scratch (optional, modes 1 / 3): >= spatial_attention_scratch_bytes(B, T, N) bytes enables the one-pass softmax of the
 // tcgen05 kernel (fix-up list of rows to recompute exactly)
 int launch_attention(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,

@@ -643,8 +643,15 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d
   return 0;
 }
 
+int device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
 int num_sms() {
-  static int n = 0;
+  static PerDevice<int> cache;
+  int& n = cache.get();
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -659,7 +666,8 @@ void set_gemm_cta_group(int cg) { g_gemm_cta_group = cg == 1 ? 1 : 2; }
 template <int kCG, int kOut, int kAct, int kLN>
 static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   using C = Cfg<kCG>;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_cache;
+  bool& attr_set = attr_cache.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kCG, kOut, kAct, kLN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);

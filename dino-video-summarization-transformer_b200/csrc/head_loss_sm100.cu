@@ -217,7 +217,8 @@ int launch_head_loss(const void* zs, const void* zt, long long ldz, const void* 
   if (P <= 0) return 0;
   if (out_dim % HN != 0 || out_dim <= 0) return set_error("head_loss: out_dim=%d must be a multiple of %d", out_dim, HN);
   if (scratch_bytes < head_loss_scratch_bytes(P)) return set_error("head_loss: scratch too small");
-  static bool attr_set = false;
+  static PerDevice<bool> attr_cache;
+  bool& attr_set = attr_cache.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
     if (e != cudaSuccess) return set_error("head_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -367,7 +367,7 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
     }
     if (i + 1 == m->cfg.depth && !get_all) {
       // Last block, CLS features only (forward() keeps norm(x)[:, 0], :342-345): nothing downstream reads the patch
-      // XX
+      // tokens' spatial-attention output, attn.proj, norm2 or MLP of this block.
       // Patch rows still provide keys / values: their K | V thirds of the qkv GEMM (N = 1536) plus the full qkv of the
       // CLS rows, then the CLS-query attention, and proj / LayerNorm / MLP on the n_cls CLS rows alone.
       const long long wrow = split ? 2LL * D : D;  // elements per weight row

@@ -25,6 +25,21 @@ import torch.nn as nn
 from . import _lib
 
 
+def _check_indices(idx, n_rows, device, validate=None):
+    """Row-gather indices of the C ABI are int32 device arrays (include/dvst.h): anything else would be read as garbage.
+    The range check costs a device sync, so it runs only when DVST_CHECK_INDICES=1 (tests) or validate=True."""
+    if idx is None:
+        raise ValueError("s_idx and t_idx must be given together")
+    if idx.dtype != torch.int32 or idx.device != device or idx.dim() != 1:
+        raise ValueError(f"row indices must be 1-D int32 tensors on {device} (got {idx.dtype} on {idx.device})")
+    idx = idx.contiguous()
+    if validate is None:
+        validate = os.environ.get("DVST_CHECK_INDICES") == "1"
+    if validate and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_rows):
+        raise IndexError(f"row index out of range [0, {n_rows})")
+    return idx
+
+
 class DINOLoss(nn.Module):
     """calculates the DINO loss for two output tensors and returns a single value (dino_similarity.py:120-135)."""
 
@@ -49,6 +64,10 @@ class DINOLoss(nn.Module):
         P = s.shape[0] if s_idx is None else s_idx.numel()
         if s_idx is None and t.shape[0] != P:
             raise ValueError("student and teacher must hold the same number of rows")
+        if s_idx is not None:
+            s_idx, t_idx = _check_indices(s_idx, s.shape[0], s.device), _check_indices(t_idx, t.shape[0], s.device)
+            if t_idx.numel() != P:
+                raise ValueError("s_idx and t_idx must have the same length")
         out = torch.empty(P, dtype=torch.float32, device=s.device)
         center = self.center.to(device=s.device, dtype=torch.float32).contiguous()
         L = _lib.lib()
@@ -101,28 +120,25 @@ def export_losses(losses_by_video, file_path):
 
 
 def preprocess_frames(video_uint8, sampling_rate=4, mean=(0.45, 0.45, 0.45), std=(0.225, 0.225, 0.225), crop_size=224):
-    """Loader front half (datasets_custom/dino_loss_loader.py:80-92): raw decoded video uint8 [n,H,W,3] -> every
-    `sampling_rate`-th frame, /255, mean/std normalised (data_utils.py:308-325), T H W C -> T C H W, centre crop
-    (transform.py:206-249, spatial_idx=1).  Runs on whatever device the video tensor lives on (upload uint8, not fp32)."""
-    if video_uint8.is_cuda and video_uint8.dtype == torch.uint8 and video_uint8.dim() == 4 and video_uint8.shape[3] == 3:
-        # one fused kernel (csrc/selection.cu: preprocess_u8_kernel) instead of four full-tensor passes
-        import ctypes
-        v = video_uint8.contiguous()
-        n, h, w = v.shape[0], v.shape[1], v.shape[2]
-        out = torch.empty(-(-n // sampling_rate), 3, crop_size, crop_size, dtype=torch.float32, device=v.device)
-        m3 = (ctypes.c_float * 3)(*[float(x) for x in mean])
-        s3 = (ctypes.c_float * 3)(*[float(x) for x in std])
-        with torch.cuda.device(v.device):
-            _lib.check(_lib.lib().dvst_preprocess_u8(_lib.ptr(v), n, h, w, sampling_rate, m3, s3, crop_size,
-                                                     _lib.ptr(out), _lib.cur_stream()))
-        return out
-    frames = video_uint8[::sampling_rate].to(torch.float32) / 255.0
-    frames = frames - torch.tensor(mean, dtype=torch.float32, device=frames.device)
-    frames = frames / torch.tensor(std, dtype=torch.float32, device=frames.device)
-    frames = frames.permute(0, 3, 1, 2)
-    h, w = frames.shape[2], frames.shape[3]
-    y0, x0 = int(math.ceil((h - crop_size) / 2)), int(math.ceil((w - crop_size) / 2))
-    return frames[:, :, y0:y0 + crop_size, x0:x0 + crop_size].contiguous()
+    """Loader front half (datasets_custom/dino_loss_loader.py:80-92): raw decoded video uint8 [n,H,W,3] (a CUDA tensor:
+    upload uint8, not fp32) -> every `sampling_rate`-th frame, /255, mean/std normalised (data_utils.py:308-325),
+    T H W C -> T C H W, centre crop (transform.py:206-249, spatial_idx=1).  One fused kernel (csrc/selection.cu:
+    preprocess_u8_kernel, bit-identical to the reference's three fp32 operations) instead of four full-tensor passes.
+    There is no CPU / PyTorch path: other inputs raise."""
+    if not (video_uint8.is_cuda and video_uint8.dtype == torch.uint8 and video_uint8.dim() == 4
+            and video_uint8.shape[3] == 3):
+        raise _lib.DvstError("preprocess_frames: expected a CUDA uint8 tensor [n,H,W,3] (decoded frames); dvst_b200 runs "
+                             "on CUDA (sm_100a) only - there is no CPU fallback")
+    import ctypes
+    v = video_uint8.contiguous()
+    n, h, w = v.shape[0], v.shape[1], v.shape[2]
+    out = torch.empty(-(-n // sampling_rate), 3, crop_size, crop_size, dtype=torch.float32, device=v.device)
+    m3 = (ctypes.c_float * 3)(*[float(x) for x in mean])
+    s3 = (ctypes.c_float * 3)(*[float(x) for x in std])
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().dvst_preprocess_u8(_lib.ptr(v), n, h, w, sampling_rate, m3, s3, crop_size,
+                                                 _lib.ptr(out), _lib.cur_stream()))
+    return out
 
 
 def window_starts(F, local_clip_size=3, global_clip_size=30):
@@ -175,7 +191,9 @@ class HeadScorer:
         zs, _ = self.head.bottleneck(feat_s)
         zt = zs if feat_t is feat_s else self.head.bottleneck(feat_t)[0]
         # gather rows per frame (tiny: [F, 256] bf16)
-        zs = zs[:, :256].index_select(0, s_idx.long()).contiguous()
+        s_idx = _check_indices(s_idx, zs.shape[0], zs.device)
+        t_idx = _check_indices(t_idx, zt.shape[0], zs.device)
+        zs = zs[:, :256].index_select(0, s_idx.long()).contiguous()   # index_select range-checks on the device
         zt = zt[:, :256].index_select(0, t_idx.long()).contiguous()
         P = zs.shape[0]
         w = self.head._packed["last_bf16"]
@@ -328,23 +346,35 @@ def score_video(model, frames, dino_loss=None, local_clip_size=3, global_clip_si
 
 def dino_similarity(cfg, local_clip_size, global_clip_size, sampling_rate, file_path, dataset=None, model=None,
                     scorer=None, videos_per_batch=8):
-    """Driver with the reference's signature (dino_similarity.py:16-93).
+    """Driver with the reference's signature and call form (dino_similarity.py:16-93):
+    `dino_similarity(args, 3, 30, 4, "loss.json")` with `args` the reference's argparse namespace (`cfg_file`, `opts`,
+    `pretrained_weights`, ...) works unchanged.
 
-    Video decoding is outside the accelerated path: `dataset` is any iterable of
-    (frames [F,3,224,224] fp32 already sub-sampled by `sampling_rate`, normalised and centre-cropped, file_name).  When
-    `model` is None it is built exactly like the reference does (get_vit_base_patch16_224 + "backbone."-stripped
-    checkpoint from cfg.pretrained_weights).  `videos_per_batch` videos are scored per backbone pass
-    (score_videos_device: same losses as one at a time) and their F-float loss vectors come back in one D2H copy each;
-    the JSON is merged once per batch (export_losses: same file content as the reference's per-video export_loss)."""
+    Like the reference, `config = load_config(cfg)` resolves the YAML + `--opts` (config.load_config; an already
+    resolved config object is used as it is), the model is get_vit_base_patch16_224 + the "backbone."-stripped
+    checkpoint `cfg.pretrained_weights`, and the videos are those listed in `<DATA.PATH_TO_DATA_DIR>/test.csv`, decoded
+    with torchvision.io.read_video (config.DecodedVideoDataset = the front half of DinoLossLoader).  What differs is where
+    the work happens: decoded uint8 frames are uploaded once, sub-sampled / normalised / cropped on the device
+    (preprocess_frames), windows are built by index, `videos_per_batch` videos are scored per backbone pass
+    (score_videos_device: same losses as one at a time) and each video's F-float loss vector comes back in one D2H copy;
+    the JSON is merged once per batch (export_losses: same file content as the reference's per-video export_loss).
+
+    Optional extensions: `dataset` = any iterable of (frames, file_name) with frames either decoded uint8 [n,H,W,3] (not
+    yet sub-sampled) or fp32 [F,3,224,224] (already sub-sampled, normalised, cropped); `model` = a prebuilt dvst_b200
+    VisionTransformer; `scorer` = a HeadScorer for mode H."""
+    from .config import DecodedVideoDataset, load_config
     from .models import get_vit_base_patch16_224
+    config = None
+    if dataset is None or model is None:
+        config = load_config(cfg)
     if dataset is None:
-        raise ValueError("pass `dataset`: an iterable of (frames, file_name); video decoding is not part of this path")
+        dataset = DecodedVideoDataset(config, "test")
     if model is None:
         # Mode R (the reference's own loss: 768-d features, tau_t = 0.02) amplifies feature error ~50x, so the model the
         # driver builds for it runs in precision="high" (per-frame loss within 1e-3 of the reference); mode H (a
         # HeadScorer) meets the same bound with bf16 operands.  DVST_PRECISION overrides; a model passed in keeps its own.
         prec = os.environ.get("DVST_PRECISION") or ("high" if scorer is None else "bf16")
-        model = get_vit_base_patch16_224(cfg=cfg, no_head=False, precision=prec)
+        model = get_vit_base_patch16_224(cfg=config, no_head=False, precision=prec)
         if getattr(cfg, "pretrained_weights", None):
             ckpt = torch.load(cfg.pretrained_weights, map_location="cpu")
             renamed = {x[len("backbone."):]: y for x, y in ckpt.items() if x.startswith("backbone.")}
@@ -364,9 +394,19 @@ def dino_similarity(cfg, local_clip_size, global_clip_size, sampling_rate, file_
             results[os.path.splitext(os.path.basename(file_name))[0]] = out[file_name]
         export_losses(out, file_path)
 
+    mean = getattr(getattr(config, "DATA", None), "MEAN", (0.45, 0.45, 0.45))
+    std = getattr(getattr(config, "DATA", None), "STD", (0.225, 0.225, 0.225))
     batch = []
-    for frames, file_name in dataset:
-        batch.append((frames.to(dev, non_blocking=True), file_name))
+    for item in dataset:
+        frames, file_name = item[0], item[1]
+        if isinstance(file_name, (list, tuple)):   # a DataLoader collates the path into a 1-list (dino_similarity.py:93)
+            file_name = file_name[0]
+        frames = frames.to(dev, non_blocking=True)
+        if frames.dtype == torch.uint8:
+            if frames.dim() == 5:                  # DataLoader batch dimension of 1
+                frames = frames[0]
+            frames = preprocess_frames(frames, sampling_rate, mean, std)
+        batch.append((frames, file_name))
         if len(batch) >= max(1, int(videos_per_batch)):
             flush(batch)
             batch = []

@@ -121,7 +121,9 @@ int dvst_head_loss(const void* zs, const void* zt, long long ldz, const void* w,
                    float teacher_temp, float student_temp, int pairs, int out_dim, float* loss, void* scratch,
                    long long scratch_bytes, void* stream);
 
-/* Same with row gathers: pair p uses student row s_idx[p] and teacher row t_idx[p] (int32 device arrays or NULL).
+/* Same with row gathers: pair p uses student row s_idx[p] and teacher row t_idx[p] (int32 DEVICE arrays, both given or
+ * both NULL; every index must lie inside its matrix - the kernel does not range-check, the Python layer validates dtype /
+ * device always and the range under DVST_CHECK_INDICES=1).
  * Covers the per-frame pairing of dino_similarity.py:87-88 over de-duplicated window features and the (iq, v != iq)
  * terms of the training DINOLoss (train_ssl.py:660-667). */
 int dvst_pair_loss_indexed(const float* student, long long lds, const int* s_idx, const float* teacher, long long ldt,
@@ -145,7 +147,9 @@ int dvst_l2norm_rows(const float* in, long long ldi, void* out, long long ldo, i
  * Replaces torch.nn.Linear as used by models/timesformer.py:41-52,63-64,71,83,108,133 and
  * vision_transformer.py:254-266.
  *   split    : 0 plain; 1 = operands hold [hi | lo] bf16 halves (lo at column K), 3-term product.
- *   bias     : fp32 [N] or NULL.   residual : fp32 [M,ldr] added before the store, or NULL (may alias out).
+ *   bias     : fp32 [N] or NULL.   residual : NULL, or the fp32 output itself (residual == out, ldr == ldo, out_kind 1):
+ *              the fused residual add is IN PLACE (out += A W^T + bias through a TMA reduce-add); any other pointer is
+ *              rejected.
  *   out_kind : 0 bf16, 1 fp32, 2 bf16 hi/lo pair (lo written at column + lo_off).   act : 0 none, 1 exact GELU. */
 int dvst_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias, int M, int N, int K,
                    int split, const float* residual, long long ldr, void* out, long long ldo, int out_kind,

@@ -262,6 +262,19 @@ def window_starts(F, local_size=3, global_size=30):
     return G, out
 
 
+def preprocess_frames(video_uint8, sampling_rate=4, mean=(0.45, 0.45, 0.45), std=(0.225, 0.225, 0.225), crop_size=224):
+    """Loader front half - datasets_custom/dino_loss_loader.py:80-92: every `sampling_rate`-th decoded frame, / 255,
+    - mean, / std as three separately rounded fp32 operations (data_utils.py:308-325), T H W C -> T C H W, centre crop
+    with ceil((H - crop) / 2) offsets (transform.py:206-249, spatial_idx = 1)."""
+    frames = video_uint8[::sampling_rate].to(torch.float32) / 255.0
+    frames = frames - torch.tensor(mean, dtype=torch.float32)
+    frames = frames / torch.tensor(std, dtype=torch.float32)
+    frames = frames.permute(0, 3, 1, 2)
+    h, w = frames.shape[2], frames.shape[3]
+    y0, x0 = int(math.ceil((h - crop_size) / 2)), int(math.ceil((w - crop_size) / 2))
+    return frames[:, :, y0:y0 + crop_size, x0:x0 + crop_size].contiguous()
+
+
 def short_video_clips(F, local_size=3):
     """Frame indices of the (student, teacher) clips every frame of a video with F < local_size sampled frames is scored
     on (dino_loss_loader.py:126-171 with len(frames) < local_size, then dino_similarity.py:78): G = F; the local slice

@@ -218,13 +218,14 @@ def test_batched_selection_matches_reference_goldens(dev, golden_dir):
 
 
 def test_fused_uint8_preprocess_is_bit_exact(dev):
-    """dvst_preprocess_u8 vs the torch CPU statement of the loader front half (dino_loss_loader.py:80-92): identical
+    """dvst_preprocess_u8 vs the oracle's CPU statement of the loader front half (dino_loss_loader.py:80-92): identical
     fp32 operations, so every value must match bit for bit (odd crop offsets and a non-multiple frame count included)."""
+    import dvst_oracle as O
     from dvst_b200.dino_similarity import preprocess_frames
     g = torch.Generator().manual_seed(0)
     for (n, H, W, rate, crop) in [(10, 240, 320, 4, 224), (7, 225, 227, 2, 224), (5, 112, 96, 1, 96)]:
         raw = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, generator=g)
-        ref = preprocess_frames(raw, rate, crop_size=crop)
+        ref = O.preprocess_frames(raw, rate, crop_size=crop)
         got = preprocess_frames(raw.to(dev), rate, crop_size=crop)
         assert got.is_cuda and tuple(got.shape) == tuple(ref.shape)
         assert torch.equal(got.cpu(), ref)

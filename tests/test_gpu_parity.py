@@ -266,15 +266,73 @@ def test_driver_function_writes_reference_json(dev, tmp_path):
             assert len(written[name]) == len(ref) and _relmax(written[name], ref) < LOSS_TOL
 
 
+def test_driver_with_the_reference_call_form(dev, tmp_path, monkeypatch):
+    """dino_similarity(args, 3, 30, 4, file_path) - the reference's exact five arguments (dino_similarity.py:16,186-189),
+    `args` being its argparse namespace (cfg_file / opts / pretrained_weights / num_workers / batch_size_per_gpu).  Decode
+    (torchvision.io.read_video) and torch.load are mocked with the same synthetic data the reference's own driver was run
+    on for tests/golden/driver_loss.json (oracle/make_golden.py:gen_driver): same keys, lengths, losses within 1e-3."""
+    import types
+    import torchvision.io as io
+    import dvst_b200.dino_similarity as ds
+    D = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "driver_loss.json")))
+    raw = {}
+    for name, meta in D["videos"].items():
+        g = torch.Generator().manual_seed(meta["seed"])
+        raw[name] = torch.randint(0, 256, (meta["n_unsampled"], 224, 224, 3), generator=g, dtype=torch.uint8)
+    (tmp_path / "test.csv").write_text("".join(f"{k}.avi 0\n" for k in D["videos"]))
+    yml = tmp_path / "cfg.yaml"
+    yml.write_text("DATA:\n  NUM_FRAMES: 8\n  TRAIN_CROP_SIZE: 224\nTIMESFORMER:\n  ATTENTION_TYPE: 'divided_space_time'\n"
+                   "TEST:\n  NUM_ENSEMBLE_VIEWS: 1\nMODEL:\n  NUM_CLASSES: 400\n")
+    args = types.SimpleNamespace(cfg_file=str(yml), pretrained_weights="synthetic.pth", num_workers=0, batch_size_per_gpu=8,
+                                 opts=["DATA.PATH_TO_DATA_DIR", str(tmp_path), "DATA.PATH_PREFIX", str(tmp_path)])
+    sd = synth_backbone_state_dict(D["seed_w"], depth=12, num_frames=8)
+    monkeypatch.setattr(io, "read_video", lambda path, pts_unit="sec": (
+        raw[os.path.splitext(os.path.basename(path))[0]], None, None), raising=False)
+    monkeypatch.setattr(ds.torch, "load", lambda *a, **k: {"backbone." + k_: v for k_, v in sd.items()})
+    out = str(tmp_path / "loss.json")
+    with torch.cuda.device(dev):
+        res = ds.dino_similarity(args, 3, 30, 4, out)
+    written = json.load(open(out))
+    assert list(written.keys()) == list(D["loss"].keys()) and written == res
+    for name, ref in D["loss"].items():
+        assert len(written[name]) == len(ref) and _relmax(written[name], ref) < LOSS_TOL
+
+
 def test_dummy_video_path(dev):
+    """Wrong crop -> the reference's dummy views (30 equal losses of the all-zero (T=3, T=60) pair)."""
     m = build(dev, 1, 2)
     with torch.no_grad():
-        a = score_video(m, torch.zeros(2, 3, 224, 224, device=dev))        # too short
         b = score_video(m, torch.randn(5, 3, 112, 112, device=dev))        # wrong crop
-    assert len(a) == 30 and len(set(a)) == 1 and a == b
+    assert len(b) == 30 and len(set(b)) == 1
     sd = synth_backbone_state_dict(1, depth=2, num_frames=8)
-    ref = O.score_video(sd, torch.zeros(2, 3, 224, 224))
-    assert len(ref) == 30 and abs(a[0] - ref[0]) / abs(ref[0]) < 5e-2
+    ref = O.score_video(sd, torch.zeros(5, 3, 112, 112))
+    assert len(ref) == 30 and abs(b[0] - ref[0]) / abs(ref[0]) < 5e-2
+
+
+def test_videos_shorter_than_the_local_window(dev):
+    """F = 1, 2 < local_clip_size = 3 are NOT dummies in the reference: its loader builds broadcast views (golden
+    windows_short.json, produced by the reference's get_views_of_video_same_size + the driver's [:, :, :3] slice):
+    student [f1, f1] vs teacher [f0, f1] for F = 2, [f0] vs [f0] for F = 1; F equal losses."""
+    from dvst_b200.dino_similarity import short_video_clips
+    W = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "windows_short.json")))
+    for F in (1, 2):
+        si, ti = short_video_clips(F, 3)
+        assert all(p["student"] == si and p["teacher"] == ti for p in W[str(F)]) and len(W[str(F)]) == F
+        assert O.short_video_clips(F, 3) == (si, ti)
+    m = build(dev, 1, 2, prec="high")
+    sd = synth_backbone_state_dict(1, depth=2, num_frames=8)
+    for F in (1, 2):
+        frames = synth_video(60 + F, F, smooth=0.5)
+        ref = O.score_video(sd, frames)
+        with torch.no_grad():
+            got = score_video(m, frames.to(dev))
+            s = m(frames[short_video_clips(F)[0]].permute(1, 0, 2, 3)[None].contiguous().to(dev))
+            t = m(frames.permute(1, 0, 2, 3)[None].contiguous().to(dev))
+            explicit = DINOLoss(768, 0.02, 0.3).to(dev).pair_losses(s, t).item()
+        assert len(got) == F == len(ref) and len(set(got)) == 1 and got[0] == explicit
+        assert _relmax(got, ref) < LOSS_TOL
+    with pytest.raises(ValueError):
+        short_video_clips(3, 5)   # 2 frames into 3: the reference's broadcast fails too
 
 
 def test_scoring_vs_oracle_and_selected_indices(dev):
@@ -322,13 +380,15 @@ def test_batched_videos_equal_one_at_a_time(dev):
     head.load_state_dict(synth_head_state_dict(2, out_dim=4096), strict=True)
     head = head.to(dev).eval()
     vids = [synth_video(s, F, smooth=0.5).to(dev) for s, F in ((1, 5), (2, 9), (3, 12), (4, 3))]
-    vids.insert(2, torch.zeros(2, 3, 224, 224, device=dev))  # too short -> dummy
+    vids.insert(2, torch.zeros(5, 3, 112, 112, device=dev))  # wrong crop -> dummy
+    vids.insert(4, synth_video(9, 2, smooth=0.5).to(dev))    # shorter than the local window -> broadcast views
     dl = DINOLoss(768, 0.02, 0.3).to(dev)
+    global_dummy = 6   # a dummy video yields `global_clip_size` losses
     for scorer in (None, HeadScorer(head, 0.04, 0.1)):
         with torch.no_grad():
             batch = score_videos_device(m, vids, dl, 3, 6, scorer=scorer)
             single = [score_video_device(m, v, dl, 3, 6, scorer=scorer) for v in vids]
-        assert [len(b) for b in batch] == [5, 9, 6, 12, 3]
+        assert [len(b) for b in batch] == [5, 9, global_dummy, 12, 2, 3]
         for b, s in zip(batch, single):
             assert torch.equal(b, s)
     assert score_videos_device(m, [], dl) == []
@@ -417,7 +477,7 @@ def test_pipeline_tool_single_gpu(dev, tmp_path):
                           "--out", str(tmp_path / "loss.json"), "--check"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "pipeline ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
     d = json.load(open(tmp_path / "loss.json"))
-    assert len(d) == 6 and len(d["video_0000"]) == 30   # the 2-frame video takes the reference's dummy path
+    assert len(d) == 6 and len(d["video_0000"]) == 2    # the 2-frame video: the reference's broadcast views, 2 losses
 
 
 def test_forward_is_cuda_graph_capturable(dev):

@@ -116,11 +116,14 @@ def test_export_losses_equals_sequential_export_loss(tmp_path):
 
 
 def test_preprocess_frames():
+    import dvst_oracle as O
     raw = torch.randint(0, 256, (10, 240, 320, 3), dtype=torch.uint8)
-    f = preprocess_frames(raw, 4)
+    f = O.preprocess_frames(raw, 4)
     assert tuple(f.shape) == (3, 3, 224, 224)
     ref = ((raw[4, 8 + 5, 48 + 7, 1].float() / 255.0) - 0.45) / 0.225
     assert abs(float(f[1, 1, 5, 7]) - float(ref)) < 1e-6
+    with pytest.raises(_lib.DvstError):       # the product has no CPU / PyTorch path for it
+        preprocess_frames(raw, 4)
 
 
 def test_sharding_is_balanced_and_complete():
@@ -157,3 +160,45 @@ def test_product_code_never_touches_the_oracle():
     pat = re.compile(r"dvst_oracle|ref_shim|make_golden|[\"'/]oracle[\"'/]|import oracle|from oracle")
     bad = [f for f in files if not f.endswith(".so") and pat.search(open(f, errors="ignore").read())]
     assert len(files) > 15 and not bad, bad
+
+
+def test_load_config_and_decoded_dataset(tmp_path, monkeypatch):
+    """config.load_config mirrors utils/parser.py:65-90 for the fields the scoring path reads (defaults, YAML, --opts);
+    config.DecodedVideoDataset mirrors the list / decode half of DinoLossLoader (dino_loss_loader.py:40-82)."""
+    import types
+    from dvst_b200.config import DecodedVideoDataset, load_config
+    yml = tmp_path / "cfg.yaml"
+    yml.write_text("DATA:\n  NUM_FRAMES: 8\n  TRAIN_CROP_SIZE: 224\nTIMESFORMER:\n  ATTENTION_TYPE: 'divided_space_time'\n"
+                   "TEST:\n  NUM_ENSEMBLE_VIEWS: 1\nMODEL:\n  NUM_CLASSES: 400\n")
+    (tmp_path / "test.csv").write_text("a.avi 0\nsub/b.avi 3\n")
+    args = types.SimpleNamespace(cfg_file=str(yml), opts=["DATA.PATH_TO_DATA_DIR", str(tmp_path), "DATA.PATH_PREFIX",
+                                                           "/videos", "DATA.USE_FLOW", "False"],
+                                 pretrained_weights="x.pth", num_workers=4, output_dir="out")
+    cfg = load_config(args)
+    assert cfg.DATA.PATH_TO_DATA_DIR == str(tmp_path) and cfg.DATA.PATH_PREFIX == "/videos" and cfg.DATA.USE_FLOW is False
+    assert cfg.DATA.MEAN == [0.45, 0.45, 0.45] and cfg.DATA.STD == [0.225, 0.225, 0.225] and cfg.DATA.NUM_FRAMES == 8
+    assert cfg.TEST.NUM_ENSEMBLE_VIEWS == 1 and cfg.MODEL.NUM_CLASSES == 400 and cfg.OUTPUT_DIR == "out"
+    assert cfg.TIMESFORMER.ATTENTION_TYPE == "divided_space_time" and cfg.TIMESFORMER.PRETRAINED_MODEL == ""
+    assert load_config(cfg) is cfg                       # an already resolved config passes through
+    assert load_config(types.SimpleNamespace(cfg_file=None, opts=None)).TEST.NUM_ENSEMBLE_VIEWS == 10   # defaults.py:96
+    ds = DecodedVideoDataset(cfg, "test")
+    assert len(ds) == 2 and ds._path_to_videos == ["/videos/a.avi", "/videos/sub/b.avi"] and ds._labels == [0, 3]
+    import torchvision.io as io
+    monkeypatch.setattr(io, "read_video", lambda path, pts_unit="sec": (torch.zeros(5, 4, 4, 3, dtype=torch.uint8), None, None),
+                        raising=False)
+    video, path = ds[1]
+    assert video.shape == (5, 4, 4, 3) and path == "/videos/sub/b.avi"
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        DecodedVideoDataset(cfg, "val")
+
+
+def test_short_video_clips_match_reference_loader_golden(golden_dir):
+    import json
+    from dvst_b200.dino_similarity import short_video_clips
+    import dvst_oracle as O
+    W = json.load(open(os.path.join(golden_dir, "windows_short.json")))
+    for F in (1, 2):
+        si, ti = short_video_clips(F, 3)
+        assert O.short_video_clips(F, 3) == (si, ti) and len(W[str(F)]) == F
+        assert all(p["student"] == si and p["teacher"] == ti for p in W[str(F)])

@@ -83,7 +83,7 @@ def test_selection_matches_reference(golden_dir):
 
 def test_driver_loop_matches_reference(golden_dir):
     """The reference's own dino_similarity() loop (loader -> views -> model -> DINOLoss -> JSON) on two tiny videos."""
-    from dvst_b200.dino_similarity import preprocess_frames
+    preprocess_frames = O.preprocess_frames
     D = json.load(open(os.path.join(golden_dir, "driver_loss.json")))
     sd = synth_backbone_state_dict(D["seed_w"], depth=12, num_frames=8)
     for name, meta in D["videos"].items():

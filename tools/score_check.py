@@ -97,7 +97,7 @@ for prec in ("bf16", "high"):
 # ---- dummy path and timing ----
 m = build("bf16")
 with torch.no_grad():
-    d = score_video(m, torch.zeros(2, 3, 224, 224, device=dev))
+    d = score_video(m, torch.zeros(5, 3, 112, 112, device=dev))  # wrong crop -> dummy views
 print("dummy video:", len(d), "values, all equal:", len(set(d)) == 1, d[0])
 ok &= len(d) == 30 and len(set(d)) == 1
 for F in (30, 68, 75):
