@@ -59,6 +59,8 @@ SIGNATURES = {
     "dvst_layernorm768": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_float,
                                   c_void_p]),
     "dvst_select_frames": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dvst_plan_windows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "dvst_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dvst_rowstats768": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p]),
     "dvst_row_offsets768": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
@@ -85,12 +87,17 @@ def lib():
                 "(there is no CPU fallback for the CUDA path)")
         l = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if not hasattr(l, name) and os.environ.get("DVST_LIB_ALLOW_MISSING") == "1":
+                continue   # same-box A/B runs against an older build of the library (DVST_LIB=...)
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
         # experiment switches (A/B runs of bench.py on one box): DVST_LN_FUSION=0 forces the stand-alone LayerNorm
         if os.environ.get("DVST_LN_FUSION") == "0":
             l.dvst_set_ln_fusion(0)
+        # DVST_ATTENTION_IMPL: 1 default (split tcgen05 kernel), 3 first-generation one-pass, 2 two-pass, 0 mma.sync
+        if os.environ.get("DVST_ATTENTION_IMPL"):
+            l.dvst_set_attention_impl(int(os.environ["DVST_ATTENTION_IMPL"]))
         _lib = l
     return _lib
 

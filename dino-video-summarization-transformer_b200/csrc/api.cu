@@ -213,6 +213,16 @@ int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
+int dvst_plan_windows(const int* lengths, int n_videos, int local_clip_size, int global_clip_size, int* s_starts,
+                      int* t_starts, int* s_idx, int* t_idx, int* n_s, int* n_t, int* n_groups, int* groups, void* stream) {
+  if (lengths == nullptr || n_s == nullptr || n_t == nullptr || n_groups == nullptr || groups == nullptr)
+    return set_error("dvst_plan_windows: null host argument");
+  if (n_videos > 0 && (s_starts == nullptr || t_starts == nullptr || s_idx == nullptr || t_idx == nullptr))
+    return set_error("dvst_plan_windows: null device argument");
+  return launch_plan_windows(lengths, n_videos, local_clip_size, global_clip_size, s_starts, t_starts, s_idx, t_idx, n_s,
+                             n_t, n_groups, groups, static_cast<cudaStream_t>(stream));
+}
+
 int dvst_knn_similarity(const float* test, long long ldt, const float* train, long long ldr, int n_test, int n_train,
                         int dim, float* sim, long long lds, void* stream) {
   if (test == nullptr || train == nullptr || sim == nullptr) return set_error("dvst_knn_similarity: null argument");

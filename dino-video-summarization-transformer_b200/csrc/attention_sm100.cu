@@ -24,111 +24,13 @@
 // softmax / epilogue of row tile A (rows 0-127), warps 8-11 of row tile B (rows 128-255).  TMEM: 2 x 256 columns; per
 // tile S occupies [0, NPAD), P overwrites [0, NPAD/2), O lands in [128, 192) once S has been consumed.
 // Shared memory: 2 stages of {Q, K, V} so the loads of problem i+1 overlap the math of problem i.
-#include "dvst_internal.h"
-#include "ptx.cuh"
+#include "attn_sm100_common.cuh"
 
 namespace dvst {
 
+using namespace attn;
+
 namespace {
-
-constexpr int HD = 64;
-constexpr int DMODEL = 768;
-constexpr int TILE_BYTES = 128 * 128;   // one 128-row tile of 128-byte rows
-constexpr int O_COL = 128;              // TMEM column of the O accumulator inside a tile's 256-column region
-constexpr int NUM_THREADS = 384;
-
-struct SpParams {
-  const __nv_bfloat16* qkv;
-  long long ld;
-  __nv_bfloat16* out;   // space-only: CLS rows are ordinary bf16 output rows
-  long long ldo;
-  float* cls_out;       // divided: [B*T, 768] fp32 CLS attention outputs (averaged over frames by the caller)
-  int mode;             // 1 divided-spatial, 3 space-only
-  int S, N, NPAD, T;
-  int n_prob, heads;
-  long long cls_base;
-  int rows_a, rows_b;   // patch rows of tile A / tile B (what the TMA stores cover)
-  int* fix_count;       // one-pass softmax: number of rows to recompute ...
-  int2* fix_list;       // ... and their (problem, row) pairs (capacity n_prob * S)
-};
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// sm_100 packed / 3-input fp32 forms: half the issue slots for the softmax's scaling, row-sum and row-max work
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpk2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// V as the B operand of O = P V: B is [N = 64 head dims] x [K = 16 keys]; in shared memory the keys are rows of 128
-// bytes (64 dims) with the TMA 128-byte swizzle, i.e. the canonical MN-major SWIZZLE_128B layout
-// ((8 chunks of 16 B along MN), (8 keys, k)) : ((1, LBO), (128 B, SBO)) with one MN atom (LBO unused) and SBO = 1024 B
-// between 8-key groups.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;            // leading byte offset (single MN atom: unused)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // stride byte offset: next group of 8 keys
-  d |= static_cast<uint64_t>(1) << 46;            // descriptor version 1 (sm_100)
-  d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
-  return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-// D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 
 template <bool kOnePass>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -536,8 +438,12 @@ __global__ void __launch_bounds__(128) attention_fixup_kernel(const SpParams p) 
 
 // 1 = tcgen05 kernel where it applies (one-pass softmax when scratch is given), 2 = tcgen05 with the two-pass softmax,
 // 0 = mma.sync kernels only
+// 3 = tcgen05 first-generation kernel with the one-pass softmax (A/B runs against the split kernel, which is what 1 picks
+// for 32 <= NPAD <= 208)
 static int g_attention_impl = 1;
-void set_attention_impl(int impl) { g_attention_impl = impl == 0 ? 0 : (impl == 2 ? 2 : 1); }
+void set_attention_impl(int impl) { g_attention_impl = impl == 0 ? 0 : (impl == 2 ? 2 : (impl == 3 ? 3 : 1)); }
+int launch_spatial_attention_split_sm100(const SpParams& p, const CUtensorMap& tmIn, const CUtensorMap& tmOutA,
+                                         const CUtensorMap& tmOutB, int grid, cudaStream_t st);
 
 // Returns 1 if the shape is not handled here (the caller falls back to the mma.sync kernels), 0 on success, < 0 error.
 long long spatial_attention_scratch_bytes(int B, int T, int N) {
@@ -583,7 +489,7 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
   // one-pass softmax needs the fix-up list: counter at scratch[0], entries from scratch + 256
   // (the choice must not depend on the batch size: one- and two-pass results differ in the last bits, and a clip's features
   // are promised to be independent of what else is in its batch)
-  const bool one_pass = g_attention_impl == 1 && scratch != nullptr && scratch_bytes >= spatial_attention_scratch_bytes(B, T, N) &&
+  const bool one_pass = (g_attention_impl == 1 || g_attention_impl == 3) && scratch != nullptr && scratch_bytes >= spatial_attention_scratch_bytes(B, T, N) &&
                         (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
   p.fix_count = static_cast<int*>(scratch);
   p.fix_list = reinterpret_cast<int2*>(static_cast<uint8_t*>(scratch) + 256);
@@ -601,7 +507,9 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
   if (one_pass) {
     cudaError_t e = cudaMemsetAsync(p.fix_count, 0, sizeof(int), st);
     if (e != cudaSuccess) return set_error("attention(sm100) memset: %s", cudaGetErrorString(e));
-    spatial_attention_sm100_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p);
+    int rc2 = g_attention_impl == 1 ? launch_spatial_attention_split_sm100(p, tmIn, tmOutA, tmOutB, grid, st) : 1;
+    if (rc2 != 0 && rc2 != 1) return rc2;
+    if (rc2 == 1) spatial_attention_sm100_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p);
     attention_fixup_kernel<<<grid < 64 ? grid : 64, 128, 0, st>>>(p);
     count_launch();
   } else {

@@ -115,10 +115,15 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
 // flash-style tcgen05 kernel for joint space-time attention (mode 2, bf16): NT = patch tokens per clip; same return codes
 int launch_joint_attention_sm100(const void* qkv, long long ld, void* out, long long ldo, int B, int NT,
                                  long long cls_base, cudaStream_t st);
-void set_attention_impl(int impl);  // 1 (default) tcgen05 (+ one-pass softmax with scratch), 2 tcgen05 two-pass, 0 mma.sync
+// 1 (default) tcgen05: split kernel (attention_split_sm100.cu) where it applies, else first generation, one-pass softmax
+// when scratch is given; 3 first generation one-pass; 2 first generation two-pass; 0 mma.sync
+void set_attention_impl(int impl);
 
 int launch_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int V, int rate,
                          int N, int* out, cudaStream_t st);
+int launch_plan_windows(const int* lengths, int n_videos, int local, int global, int* s_starts, int* t_starts,
+                        int* s_idx, int* t_idx, int* n_s_out, int* n_t_out, int* n_groups_out, int* groups_out,
+                        cudaStream_t st);
 int launch_preprocess_u8(const uint8_t* video, int n, int H, int W, int rate, const float* mean3, const float* std3,
                          int crop, float* out, cudaStream_t st);
 

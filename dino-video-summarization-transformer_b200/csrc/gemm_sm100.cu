@@ -240,7 +240,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_iters = p.split ? 3 * nk : nk;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      // (the whole warp walks the loop; one elected lane issues - see elect_one() in ptx.cuh)
       int s = 0;
       uint32_t ph = 0;
       // TMA completion bytes of BOTH CTAs are signalled on the leader's `full` barrier
@@ -260,21 +261,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ka = kb = it * BK;
           }
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
-          if (kCG == 1) {
-            mbar_arrive_expect_tx(full_bar + 8 * s, C::STAGE_BYTES);
-            tma_load_2d(sA + s * A_BYTES, &tmA, full_bar + 8 * s, ka, row_a);
-            tma_load_2d(sB + s * C::B_BYTES, &tmB, full_bar + 8 * s, kb, row_b);
-          } else {
-            if (leader) mbar_arrive_expect_tx(full_bar + 8 * s, 2 * C::STAGE_BYTES);
-            tma_load_2d_cg2(sA + s * A_BYTES, &tmA, full_leader + 8 * s, ka, row_a);
-            tma_load_2d_cg2(sB + s * C::B_BYTES, &tmB, full_leader + 8 * s, kb, row_b);
+          if (elect_one()) {
+            if (kCG == 1) {
+              mbar_arrive_expect_tx(full_bar + 8 * s, C::STAGE_BYTES);
+              tma_load_2d(sA + s * A_BYTES, &tmA, full_bar + 8 * s, ka, row_a);
+              tma_load_2d(sB + s * C::B_BYTES, &tmB, full_bar + 8 * s, kb, row_b);
+            } else {
+              if (leader) mbar_arrive_expect_tx(full_bar + 8 * s, 2 * C::STAGE_BYTES);
+              tma_load_2d_cg2(sA + s * A_BYTES, &tmA, full_leader + 8 * s, ka, row_a);
+              tma_load_2d_cg2(sB + s * C::B_BYTES, &tmB, full_leader + 8 * s, kb, row_b);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(BM * kCG, BN);
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
@@ -287,15 +290,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t a_addr = sA + s * A_BYTES;
           const uint32_t b_addr = sB + s * C::B_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16<kCG>(tmem_d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
-                           idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16<kCG>(tmem_d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32),
+                             idesc, (it | k) != 0 ? 1u : 0u);
+            }
+            if (kCG == 1) umma_commit(empty_bar + 8 * s); else umma_commit_cg2(empty_bar + 8 * s, 3);
+            if (it == num_iters - 1) {
+              if (kCG == 1) umma_commit(tfull_bar + 8 * a); else umma_commit_cg2(tfull_bar + 8 * a, 3);
+            }
           }
-          if (kCG == 1) umma_commit(empty_bar + 8 * s); else umma_commit_cg2(empty_bar + 8 * s, 3);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (kCG == 1) umma_commit(tfull_bar + 8 * a); else umma_commit_cg2(tfull_bar + 8 * a, 3);
         if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
       }
     }
@@ -314,7 +321,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     auto stage_and_store = [&](const uint32_t (&w)[32], int gcol, int grow) {
       // the TMA store issued STG_BUFS boxes ago must have finished reading this buffer
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(STG_BUFS - 1) : "memory");
+      if (elect_one()) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(STG_BUFS - 1) : "memory");
       __syncwarp();
       const uint32_t dst = stg + buf * STG_BUF_BYTES + row_off;
 #pragma unroll
@@ -323,7 +330,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                      "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3]) : "memory");
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t src = stg + buf * STG_BUF_BYTES;
         if (p.accumulate)
           asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
@@ -364,7 +371,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++l_c == NCH) { l_c = 0; l_tile += tile_step; }
           }
         };
-        if (lane == 0) { issue_load(); issue_load(); }
+        if (elect_one()) { issue_load(); issue_load(); }
         uint32_t g = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
           const int m_blk = tile / p.num_n_blocks;
@@ -428,7 +435,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            : "memory");
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                            ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(ring + sl * STG_BUF_BYTES), "r"(gcol0), "r"(grow)
                            : "memory");
@@ -453,7 +460,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
     } else {
@@ -572,7 +579,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
     }  // not a producer
   }

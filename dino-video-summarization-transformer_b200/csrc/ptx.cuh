@@ -18,6 +18,17 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// elect.sync: true in exactly one lane (the lowest) of a converged warp.  Guard single-thread tcgen05 / TMA issue with
+// this instead of `lane == 0`: ptxas then knows the guarded instruction runs in one lane and feeds it from the uniform
+// datapath directly.  Under a plain lane test it wraps EVERY tcgen05.mma / cp.async.bulk.tensor in an ELECT / BRA.U.ANY
+// "waterfall" loop with R2UR moves - ~20 extra instructions and ~85 clk per issued instruction (measured in round 2: a
+// 13-step P V chain took 1 500 - 1 800 clk to issue, 590 with elect.sync).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -2,9 +2,16 @@
 //   * select_frames_kernel   - adaptive frame selection (datasets_custom/frame_selection_loader.py:115-172) for a whole
 //                              batch of videos, one thread per video, in the reference's fp64 arithmetic (numpy pairwise
 //                              np.sum, sequential np.cumsum, first-minimum argmin) so the index lists are identical;
+//   * plan_windows_kernel    - the loader's window rule (dino_loss_loader.py:126-171) for a batch of videos as index
+//                              arithmetic on the device: distinct (local, global) window starts and the per-frame rows
+//                              into them - the video lengths travel as kernel parameters, so planning a batch needs no
+//                              host-to-device copy and no synchronisation (and is CUDA-graph capturable);
 //   * preprocess_u8_kernel   - loader front half (dino_loss_loader.py:80-92): every rate-th frame of the decoded uint8
 //                              [n, H, W, 3] video -> / 255, - mean, / std (data_utils.py:308-325, same three fp32
 //                              operations), T H W C -> T C H W, centre crop (transform.py:228-229): one pass, fp32 out.
+#include <algorithm>
+#include <vector>
+
 #include "dvst_internal.h"
 
 namespace dvst {
@@ -95,6 +102,31 @@ __global__ void select_frames_kernel(const double* __restrict__ loss, long long 
   }
 }
 
+// One block per video.  Exactly the reference's clamp code (dino_loss_loader.py:137-156): j = i - loc, k = i + loc + 1,
+// l = i - glob, m = i + glob; j < 0 -> (0, local); k >= F -> (F - local, F); l < 0 -> (0, G); m >= F -> (F - G, F).
+// With F >= local the distinct local starts are exactly 0 .. F - local and the distinct global starts 0 .. F - G, so the
+// row of a window inside its list is its start.
+struct PlanVideo { int off, F, G, base_s, base_t; };
+constexpr int PLAN_CHUNK = 128;
+struct PlanBatch { PlanVideo v[PLAN_CHUNK]; };
+
+__global__ void plan_windows_kernel(const PlanBatch pb, int local, int global, int* __restrict__ s_starts,
+                                    int* __restrict__ t_starts, int* __restrict__ s_idx, int* __restrict__ t_idx) {
+  const PlanVideo v = pb.v[blockIdx.x];
+  const int loc = local / 2, glob = global / 2;
+  for (int i = threadIdx.x; i < v.F; i += blockDim.x) {
+    int j = i - loc, k = i + loc + 1, l = i - glob, m = i + glob;
+    if (j < 0) { j = 0; k = local; }
+    if (k >= v.F) { k = v.F; j = v.F - local; }
+    if (l < 0) { l = 0; m = v.G; }
+    if (m >= v.F) { m = v.F; l = v.F - v.G; }
+    s_idx[v.off + i] = v.base_s + j;
+    t_idx[v.off + i] = v.base_t + l;
+  }
+  for (int j = threadIdx.x; j <= v.F - local; j += blockDim.x) s_starts[v.base_s + j] = v.off + j;
+  for (int l = threadIdx.x; l <= v.F - v.G; l += blockDim.x) t_starts[v.base_t + l] = v.off + l;
+}
+
 __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ video, int H, int W, int rate, int F, int crop, int y0,
                                      int x0, float m0, float m1, float m2, float s0, float s1, float s2,
                                      float* __restrict__ out) {
@@ -126,6 +158,55 @@ int launch_select_frames(const double* loss, long long ld, const int* n_loss, co
   count_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : set_error("select_frames launch: %s", cudaGetErrorString(e));
+}
+
+int launch_plan_windows(const int* lengths, int n_videos, int local, int global, int* s_starts, int* t_starts,
+                        int* s_idx, int* t_idx, int* n_s_out, int* n_t_out, int* n_groups_out, int* groups_out,
+                        cudaStream_t st) {
+  if (n_videos <= 0) { *n_s_out = *n_t_out = *n_groups_out = 0; return 0; }
+  if (local <= 0 || global <= 0) return set_error("plan_windows: bad window sizes %d / %d", local, global);
+  // groups: distinct teacher window lengths G = min(global, F), ascending; each group's windows are contiguous rows
+  std::vector<int> Gs;
+  for (int v = 0; v < n_videos; ++v) {
+    if (lengths[v] < local) return set_error("plan_windows: video %d has %d frames, fewer than the local window %d", v, lengths[v], local);
+    const int G = lengths[v] < global ? lengths[v] : global;
+    if (std::find(Gs.begin(), Gs.end(), G) == Gs.end()) Gs.push_back(G);
+  }
+  std::sort(Gs.begin(), Gs.end());
+  std::vector<int> gcount(Gs.size(), 0), gbase(Gs.size(), 0);
+  for (int v = 0; v < n_videos; ++v) {
+    const int F = lengths[v], G = F < global ? F : global;
+    gcount[std::lower_bound(Gs.begin(), Gs.end(), G) - Gs.begin()] += F - G + 1;
+  }
+  int n_t = 0;
+  for (size_t g = 0; g < Gs.size(); ++g) { gbase[g] = n_t; n_t += gcount[g]; }
+  std::vector<int> gfill(gbase);
+  long long off = 0, n_s = 0;
+  for (int v0 = 0; v0 < n_videos; v0 += PLAN_CHUNK) {
+    PlanBatch pb;
+    const int nv = n_videos - v0 < PLAN_CHUNK ? n_videos - v0 : PLAN_CHUNK;
+    for (int u = 0; u < nv; ++u) {
+      const int F = lengths[v0 + u], G = F < global ? F : global;
+      const size_t g = std::lower_bound(Gs.begin(), Gs.end(), G) - Gs.begin();
+      if (off + F > 0x7FFFFFFFLL) return set_error("plan_windows: too many frames");
+      pb.v[u] = PlanVideo{static_cast<int>(off), F, G, static_cast<int>(n_s), gfill[g]};
+      gfill[g] += F - G + 1;
+      n_s += F - local + 1;
+      off += F;
+    }
+    plan_windows_kernel<<<nv, 128, 0, st>>>(pb, local, global, s_starts, t_starts, s_idx, t_idx);
+    count_launch();
+  }
+  *n_s_out = static_cast<int>(n_s);
+  *n_t_out = n_t;
+  *n_groups_out = static_cast<int>(Gs.size());
+  for (size_t g = 0; g < Gs.size(); ++g) {
+    groups_out[3 * g] = Gs[g];
+    groups_out[3 * g + 1] = gcount[g];
+    groups_out[3 * g + 2] = gbase[g];
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : set_error("plan_windows launch: %s", cudaGetErrorString(e));
 }
 
 int launch_preprocess_u8(const uint8_t* video, int n, int H, int W, int rate, const float* mean3, const float* std3,

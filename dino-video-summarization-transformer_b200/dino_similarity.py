@@ -207,15 +207,22 @@ class HeadScorer:
         return loss
 
 
-def _forward_windows(model, frames, starts, T, max_clips):
-    """Features [len(starts), 768] of the T-frame windows of `frames` [F,3,H,W] starting at `starts` (python ints)."""
+def _forward_windows(model, frames, starts, T, max_clips, out=None):
+    """Features [n, 768] of the T-frame windows of `frames` [F,3,H,W] starting at `starts` (python ints, or an int32
+    CUDA tensor as written by dvst_plan_windows - then nothing is copied from the host)."""
     L = _lib.lib()
     dev = frames.device
     model._ensure_packed(dev)
     F, _, H, W = frames.shape
-    n = len(starts)
-    out = torch.empty(n, model.embed_dim, dtype=torch.float32, device=dev)
-    starts_t = torch.tensor(starts, dtype=torch.int32, device=dev)
+    if torch.is_tensor(starts):
+        if starts.dtype != torch.int32 or starts.device != dev:
+            raise ValueError("window starts must be an int32 tensor on the frames' device")
+        starts_t = starts.contiguous()
+    else:
+        starts_t = torch.tensor(starts, dtype=torch.int32, device=dev)
+    n = starts_t.numel()
+    if out is None:
+        out = torch.empty(n, model.embed_dim, dtype=torch.float32, device=dev)
     for c0 in range(0, n, max_clips):
         nb = min(max_clips, n - c0)
         need = L.dvst_workspace_bytes(model._handle, nb, T, H, W)
@@ -226,6 +233,30 @@ def _forward_windows(model, frames, starts, T, max_clips):
                                           _lib.ptr(out[c0:]), _lib.ptr(model._workspace), model._workspace.numel(),
                                           _lib.cur_stream()))
     return out
+
+
+def plan_windows(lengths, local_clip_size, global_clip_size, device):
+    """dvst_plan_windows: the loader's window rule for a batch of videos (concatenated along the frame axis) as device
+    index arrays.  Returns (s_starts, t_starts, s_idx, t_idx, groups) with groups = [(G, n_windows, first_row), ...]
+    ascending in G.  The lengths travel as kernel parameters: no host-to-device copy, no synchronisation."""
+    import ctypes
+    n = len(lengths)
+    n_s = sum(F - local_clip_size + 1 for F in lengths)
+    n_t = sum(F - min(global_clip_size, F) + 1 for F in lengths)
+    total = sum(lengths)
+    buf = torch.empty(n_s + n_t + 2 * total, dtype=torch.int32, device=device)
+    s_starts, t_starts = buf[:n_s], buf[n_s:n_s + n_t]
+    s_idx, t_idx = buf[n_s + n_t:n_s + n_t + total], buf[n_s + n_t + total:]
+    arr = (ctypes.c_int * n)(*[int(F) for F in lengths])
+    o_ns, o_nt, o_ng = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    groups = (ctypes.c_int * (3 * n))()
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().dvst_plan_windows(arr, n, int(local_clip_size), int(global_clip_size), _lib.ptr(s_starts),
+                                                _lib.ptr(t_starts), _lib.ptr(s_idx), _lib.ptr(t_idx), ctypes.byref(o_ns),
+                                                ctypes.byref(o_nt), ctypes.byref(o_ng), groups, _lib.cur_stream()))
+    assert o_ns.value == n_s and o_nt.value == n_t
+    return s_starts, t_starts, s_idx, t_idx, [(groups[3 * g], groups[3 * g + 1], groups[3 * g + 2])
+                                               for g in range(o_ng.value)]
 
 
 def _dummy_losses(model, dev, dino_loss, scorer, local_clip_size, global_clip_size):
@@ -288,37 +319,15 @@ def score_videos_device(model, videos, dino_loss, local_clip_size=3, global_clip
         frames = clips[0] if len(clips) == 1 else torch.cat(clips, 0)
         H, W = frames.shape[2], frames.shape[3]
         N = (H // 16) * (W // 16)
-        # window starts in units of the concatenated frame axis; windows never cross a video boundary because every
-        # start is clamped to [0, F_v - T] inside its own video (window_starts)
-        s_starts, s_idx = [], []
-        t_starts, t_idx = {}, []       # G -> distinct starts; per frame (G, position inside that G's list)
-        lengths, off = [], 0
-        for c in clips:
-            F = c.shape[0]
-            G, ls, gs = window_starts(F, local_clip_size, global_clip_size)
-            s_pos = {}
-            for j in sorted(set(ls)):
-                s_pos[j] = len(s_starts)
-                s_starts.append(off + j)
-            s_idx += [s_pos[j] for j in ls]
-            lst = t_starts.setdefault(G, [])
-            t_pos = {}
-            for l in sorted(set(gs)):
-                t_pos[l] = len(lst)
-                lst.append(off + l)
-            t_idx += [(G, t_pos[l]) for l in gs]
-            lengths.append(F)
-            off += F
+        lengths = [c.shape[0] for c in clips]
+        # window starts in units of the concatenated frame axis (windows never cross a video boundary: every start is
+        # clamped to [0, F_v - T] inside its own video); built on the device, no host round trip
+        s_starts, t_starts, s_idx_t, t_idx_t, groups = plan_windows(lengths, local_clip_size, global_clip_size, dev)
         fs = _forward_windows(model, frames, s_starts, local_clip_size, max(1, max_rows // (N * local_clip_size)))
-        base, parts = {}, []
-        row = 0
-        for G in sorted(t_starts):
-            base[G] = row
-            parts.append(_forward_windows(model, frames, t_starts[G], G, max(1, max_rows // (N * G))))
-            row += len(t_starts[G])
-        ft = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
-        s_idx_t = torch.tensor(s_idx, dtype=torch.int32, device=dev)
-        t_idx_t = torch.tensor([base[G] + p for G, p in t_idx], dtype=torch.int32, device=dev)
+        ft = torch.empty(t_starts.numel(), model.embed_dim, dtype=torch.float32, device=dev)
+        for G, cnt, row0 in groups:
+            _forward_windows(model, frames, t_starts[row0:row0 + cnt], G, max(1, max_rows // (N * G)),
+                             out=ft[row0:row0 + cnt])
         if scorer is not None:
             loss = scorer.pair_losses(fs, ft, s_idx_t, t_idx_t)
         else:

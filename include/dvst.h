@@ -200,6 +200,20 @@ int dvst_attention_ws(const void* qkv, long long ld, void* out, long long ldo, f
 int dvst_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int n_videos,
                        int pre_sampling_rate, int num_frames, int* indices, void* stream);
 
+/* Window plan of a batch of videos: get_views_of_video_same_size (datasets_custom/dino_loss_loader.py:126-171) as index
+ * arithmetic on the device, for videos concatenated along the frame axis.  Replaces the [2F,3,G,224,224] view tensors and
+ * the per-video Python loop: identical windows are listed once (F - local + 1 distinct local and F - G + 1 distinct global
+ * windows per video, G = min(global, F)).
+ *   lengths   HOST int [n_videos]: sampled frames per video, each >= local_clip_size (they travel as kernel parameters:
+ *             no host-to-device copy, no synchronisation, capturable in a CUDA graph)
+ *   s_starts  DEVICE int32 [sum(F - local + 1)]: first frame (concatenated axis) of every distinct local window, video-major
+ *   t_starts  DEVICE int32 [sum(F - G + 1)]: the same for the global windows, grouped by G ascending, video-major inside
+ *   s_idx, t_idx  DEVICE int32 [sum F]: per frame, the row of its local / global window in those lists
+ *   n_s, n_t, n_groups, groups  HOST outputs: list lengths, number of distinct G, and (G, windows, first row) per group
+ *             (groups holds 3 * n_videos ints at most) - what the caller needs to issue one dvst_forward_windows per G. */
+int dvst_plan_windows(const int* lengths, int n_videos, int local_clip_size, int global_clip_size, int* s_starts,
+                      int* t_starts, int* s_idx, int* t_idx, int* n_s, int* n_t, int* n_groups, int* groups, void* stream);
+
 /* Loader front half (datasets_custom/dino_loss_loader.py:80-92) in one pass: decoded video uint8 [n_frames, H, W, 3]
  * (device) -> every sampling_rate-th frame, / 255, - mean, / std (data_utils.py:308-325), T H W C -> T C H W, centre crop
  * (transform.py:228-229): frames fp32 [ceil(n_frames / sampling_rate), 3, crop, crop].  mean3 / std3 are HOST pointers. */

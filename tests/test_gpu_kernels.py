@@ -399,12 +399,19 @@ def test_deferred_layernorm_row_offsets_keep_large_mean_rows_accurate(dev):
 @pytest.mark.parametrize("mode,B,T,N,adversarial", [(1, 5, 5, 196, False), (3, 5, 5, 196, False), (1, 5, 5, 36, False),
                                                      (1, 5, 5, 196, True), (3, 5, 5, 196, True), (1, 5, 5, 36, True),
                                                      (1, 5, 5, 196, "sink"), (3, 5, 5, 196, "sink"), (1, 1, 2, 196, False)])
-def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
-    """tcgen05 spatial attention with scratch: softmax referenced to the maximum of the first 32 keys.  Ordinary inputs
-    need no fix-up; adversarial ones (row maxima hundreds of nats above those 32 keys: exp2 overflows) are recomputed
-    exactly by the fix-up kernel - both must match the fp32 reference."""
+@pytest.mark.parametrize("impl", [1, 3])
+def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial, impl):
+    """tcgen05 spatial attention with scratch: softmax referenced to the maximum of a 32-key sample and the CLS key (the
+    split kernel, impl 1: the first 32 keys of its second key half; the first-generation kernel, impl 3: the first 32
+    keys).  Ordinary inputs need no fix-up; adversarial ones (row maxima hundreds of nats above the sample: exp2
+    overflows) are recomputed exactly by the fix-up kernel - both must match the fp32 reference."""
     torch.manual_seed(7 + mode + N)
     L = _lib.lib()
+    npad = (N + 1 + 15) & ~15
+    k0 = ((npad // 2) + 15) & ~15
+    split = impl == 1 and 32 <= npad <= 208
+    # key positions outside the kernel's reference sample
+    far_pos = [p for p in range(N) if (p >= 8 and not (k0 <= p < k0 + 32))] if split else list(range(min(40, N - 1), N))
     Mt = B * N * T
     ncls = B * T if mode == 3 else B
     qkv = (torch.randn(Mt + ncls, 2304, device=dev) * 1.5).bfloat16()
@@ -420,7 +427,7 @@ def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
         # query does too -> scores ~ +-2000 / 8 far above anything among the first 32 keys
         u = torch.nn.functional.normalize(torch.randn(64, device=dev), dim=0)
         rows = torch.arange(Mt, device=dev).reshape(B, N, T)
-        far_keys = rows[:, min(40, N - 1):, :].reshape(-1)
+        far_keys = rows[:, far_pos, :].reshape(-1)
         for h in range(12):
             qkv[far_keys, 768 + h * 64: 768 + (h + 1) * 64] = (45.0 * u).bfloat16()
             qkv[Mt:, 768 + h * 64: 768 + (h + 1) * 64] = (-45.0 * u).bfloat16()
@@ -430,8 +437,12 @@ def test_attention_one_pass_softmax_and_fixup(dev, mode, B, T, N, adversarial):
     scratch = torch.zeros(nb, dtype=torch.uint8, device=dev)
     out = torch.zeros(Mt + ncls, 768, device=dev, dtype=torch.bfloat16)
     cls_out = torch.zeros(B, T, 768, device=dev)
-    _lib.check(L.dvst_attention_ws(_lib.ptr(qkv), 2304, _lib.ptr(out), 768, _lib.ptr(cls_out), mode, B, T, N, Mt,
-                                   _lib.ptr(scratch), nb, _lib.cur_stream()))
+    try:
+        L.dvst_set_attention_impl(impl)
+        _lib.check(L.dvst_attention_ws(_lib.ptr(qkv), 2304, _lib.ptr(out), 768, _lib.ptr(cls_out), mode, B, T, N, Mt,
+                                       _lib.ptr(scratch), nb, _lib.cur_stream()))
+    finally:
+        L.dvst_set_attention_impl(1)
     n_fix = int(scratch[:4].view(torch.int32)[0])
     assert (n_fix > 0) == (adversarial is True)
     q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
