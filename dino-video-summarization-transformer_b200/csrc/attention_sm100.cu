@@ -113,7 +113,7 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
       if (lane == 0) mbar_wait(empty_bar + 8 * s, ph ^ 1);
       __syncwarp();
       const uint32_t st = base + s * stage_bytes;
-      if (lane == 0) {
+      if (elect_one()) {
         tma_load_3d(st, &tmIn, full_bar + 8 * s, head * HD, t, b * N);
         tma_load_3d(st + q_bytes, &tmIn, full_bar + 8 * s, DMODEL + head * HD, t, b * N);
         tma_load_3d(st + q_bytes + kv_bytes, &tmIn, full_bar + 8 * s, 2 * DMODEL + head * HD, t, b * N);
@@ -130,18 +130,20 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
       if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * s, 3u * N * 128u);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer (whole warp in the loop, one elected lane issues - elect_one() in ptx.cuh) =====
       const uint32_t idesc_s = make_idesc(128, NPAD, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, HD, 1);
       const int ksteps = NPAD >> 4;
       auto issue_s = [&](int tile, uint32_t st) {
         const uint32_t d = tmem_base + tile * 256;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16<1>(d, make_kmajor_sw128_desc(st + tile * TILE_BYTES + k * 32),
-                       make_kmajor_sw128_desc(st + q_bytes + k * 32), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(sfull_bar + 8 * tile);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16<1>(d, make_kmajor_sw128_desc(st + tile * TILE_BYTES + k * 32),
+                         make_kmajor_sw128_desc(st + q_bytes + k * 32), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(sfull_bar + 8 * tile);
+        }
       };
       // Software-pipelined issue order: S of problem i+1 for a row tile goes out as soon as that tile's O of problem i
       // has been read back, i.e. BEFORE waiting for the other tile's P - the two tiles' chains
@@ -163,11 +165,16 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
           mbar_wait(pfull_bar + 8 * tile, tp);
           tc_fence_after();
           const uint32_t region = tmem_base + tile * 256;
-          for (int j = 0; j < ksteps; ++j)
-            umma_ts_bf16(region + O_COL, region + j * 8, make_mnmajor_sw128_desc(st + q_bytes + kv_bytes + j * 2048),
-                         idesc_pv, j != 0 ? 1u : 0u);
-          umma_commit(ofull_bar + 8 * tile);
-          if (tile == n_tiles - 1) umma_commit(empty_bar + 8 * s);  // every MMA reading this stage has been issued
+          if (elect_one()) {
+            const uint64_t vdesc0 = make_mnmajor_sw128_desc(st + q_bytes + kv_bytes);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < ksteps)
+                umma_ts_bf16(region + O_COL, region + j * 8, vdesc0 + static_cast<uint64_t>(j * 128), idesc_pv,
+                             j != 0 ? 1u : 0u);
+            umma_commit(ofull_bar + 8 * tile);
+            if (tile == n_tiles - 1) umma_commit(empty_bar + 8 * s);  // every MMA reading this stage has been issued
+          }
           if (has_next) {
             if (tile == 0) {
               mbar_wait(full_bar + 8 * s_next, ph_next);
@@ -663,7 +670,7 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
       if (t >= n_tiles) return 0u;                       // inactive second Q tile of the last block
       const int row0 = b * p.NT + t * 128;
       if (t < n_tiles - 1) {
-        if (lane == 0) tma_load_2d(dst, &tmFull, bar, col, row0);
+        if (elect_one()) tma_load_2d(dst, &tmFull, bar, col, row0);
         return JT_TILE;
       }
       if (p.rem > 0 && lane == 0) tma_load_2d(dst, &tmRem, bar, col, row0);
@@ -698,8 +705,12 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer: the whole warp runs the state machine (every poll result is lane 0's, so the control flow stays
+      // warp-uniform), one elected lane issues - no per-instruction waterfall loops (elect_one() in ptx.cuh) =====
+      auto try_wait_u = [&](uint32_t bar, uint32_t parity) -> bool {
+        return __shfl_sync(0xFFFFFFFFu, mbar_try_wait(bar, parity) ? 1 : 0, 0) != 0;
+      };
       constexpr uint32_t idesc_s = make_idesc(128, 128, 0);
       constexpr uint32_t idesc_pv = make_idesc(128, HD, 1);
       // The two Q tiles run decoupled: whenever a tile's P of key tile j is ready, its P V (j) and right behind it its
@@ -713,11 +724,13 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
         tc_fence_after();
         const uint32_t aK = sKV + s * 2 * JT_TILE;
         const uint32_t d = tmem_base + tile * 256;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16<1>(d, make_kmajor_sw128_desc(sQ + tile * JT_TILE + k * 32), make_kmajor_sw128_desc(aK + k * 32),
-                       idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(s_full + 8 * tile);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16<1>(d, make_kmajor_sw128_desc(sQ + tile * JT_TILE + k * 32), make_kmajor_sw128_desc(aK + k * 32),
+                         idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(s_full + 8 * tile);
+        }
       };
       for (int prob = blockIdx.x; prob < p.n_prob; prob += gridDim.x, ++pi) {
         mbar_wait(q_full, pi & 1);
@@ -734,12 +747,12 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
             const uint32_t it = kv_base + j;
             const int s = it % JT_STAGES;
             if (need_s[tile]) {
-              if (!mbar_try_wait(kv_full + 8 * s, (it / JT_STAGES) & 1)) continue;
+              if (!try_wait_u(kv_full + 8 * s, (it / JT_STAGES) & 1)) continue;
               issue_s(tile, it);
               need_s[tile] = false;
               continue;
             }
-            if (!mbar_try_wait(p_full + 8 * tile, (bcs + j) & 1)) continue;
+            if (!try_wait_u(p_full + 8 * tile, (bcs + j) & 1)) continue;
             // (the softmax warps release O of the previous problem on their own: this wait cannot involve the other tile)
             if (j == 0 && pi > 0) mbar_wait(o_empty + 8 * tile, (pi - 1) & 1);
             tc_fence_after();
@@ -747,25 +760,27 @@ joint_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmFull, const _
             bool next_s_issued = false;
             if (j + 1 < n_tiles) {
               const uint32_t itn = it + 1;
-              if (mbar_try_wait(kv_full + 8 * (itn % JT_STAGES), (itn / JT_STAGES) & 1)) {
+              if (try_wait_u(kv_full + 8 * (itn % JT_STAGES), (itn / JT_STAGES) & 1)) {
                 issue_s(tile, itn);
                 next_s_issued = true;
               }
             }
             const uint32_t aV = sKV + s * 2 * JT_TILE + JT_TILE;
             const uint32_t region = tmem_base + tile * 256;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_ts_bf16(region + JT_O_COL, region + JT_P_COL + k * 8, make_mnmajor_sw128_desc(aV + k * 2048), idesc_pv,
-                           (j | k) != 0 ? 1u : 0u);
-            umma_commit(o_full + 8 * tile);
-            // the stage is free once BOTH tiles' MMAs on it have completed: the later of the two commits it
-            if (jt[tile ^ 1] > j) umma_commit(kv_empty + 8 * s);
+              for (int k = 0; k < 8; ++k)
+                umma_ts_bf16(region + JT_O_COL, region + JT_P_COL + k * 8, make_mnmajor_sw128_desc(aV + k * 2048), idesc_pv,
+                             (j | k) != 0 ? 1u : 0u);
+              umma_commit(o_full + 8 * tile);
+              // the stage is free once BOTH tiles' MMAs on it have completed: the later of the two commits it
+              if (jt[tile ^ 1] > j) umma_commit(kv_empty + 8 * s);
+            }
             jt[tile] = j + 1;
             need_s[tile] = !next_s_issued;
           }
         }
-        umma_commit(q_empty);
+        if (elect_one()) umma_commit(q_empty);
         kv_base += n_tiles;
         bcs += n_tiles;
       }

@@ -73,23 +73,30 @@ head_loss_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(a_bar, 2 * A_BYTES_ALL);
-      for (int kb = 0; kb < HKB; ++kb) {
-        tma_load_2d(sAs + kb * A_TILE_BYTES, &tmS, a_bar, kb * 64, m_tile * HM);
-        tma_load_2d(sAt + kb * A_TILE_BYTES, &tmT, a_bar, kb * 64, m_tile * HM);
+    {
+      // (whole warp in the loop, one elected lane issues: no per-instruction waterfall loops - elect_one() in ptx.cuh)
+      if (elect_one()) {
+        mbar_arrive_expect_tx(a_bar, 2 * A_BYTES_ALL);
+#pragma unroll
+        for (int kb = 0; kb < HKB; ++kb) {
+          tma_load_2d(sAs + kb * A_TILE_BYTES, &tmS, a_bar, kb * 64, m_tile * HM);
+          tma_load_2d(sAt + kb * A_TILE_BYTES, &tmT, a_bar, kb * 64, m_tile * HM);
+        }
       }
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        mbar_arrive_expect_tx(full_bar + 8 * s, W_STAGE_BYTES);
-        for (int kb = 0; kb < HKB; ++kb)
-          tma_load_2d(sW + s * W_STAGE_BYTES + kb * W_TILE_BYTES, &tmW, full_bar + 8 * s, kb * 64, tile * HN);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar + 8 * s, W_STAGE_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < HKB; ++kb)
+            tma_load_2d(sW + s * W_STAGE_BYTES + kb * W_TILE_BYTES, &tmW, full_bar + 8 * s, kb * 64, tile * HN);
+        }
         if (++s == HSTAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16_f32(HM, HN);
       mbar_wait(a_bar, 0);
       tc_fence_after();
@@ -99,17 +106,19 @@ head_loss_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         mbar_wait(full_bar + 8 * s, ph);
         tc_fence_after();
         const uint32_t d_s = tmem_base + a * 128, d_t = d_s + 64;
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < HKB; ++kb) {
+          for (int kb = 0; kb < HKB; ++kb) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t wdesc = make_kmajor_sw128_desc(sW + s * W_STAGE_BYTES + kb * W_TILE_BYTES + k * 32);
-            umma_bf16<1>(d_s, make_kmajor_sw128_desc(sAs + kb * A_TILE_BYTES + k * 32), wdesc, idesc, (kb | k) != 0);
-            umma_bf16<1>(d_t, make_kmajor_sw128_desc(sAt + kb * A_TILE_BYTES + k * 32), wdesc, idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t wdesc = make_kmajor_sw128_desc(sW + s * W_STAGE_BYTES + kb * W_TILE_BYTES + k * 32);
+              umma_bf16<1>(d_s, make_kmajor_sw128_desc(sAs + kb * A_TILE_BYTES + k * 32), wdesc, idesc, (kb | k) != 0);
+              umma_bf16<1>(d_t, make_kmajor_sw128_desc(sAt + kb * A_TILE_BYTES + k * 32), wdesc, idesc, (kb | k) != 0);
+            }
           }
+          umma_commit(empty_bar + 8 * s);
+          umma_commit(tfull_bar + 8 * a);
         }
-        umma_commit(empty_bar + 8 * s);
-        umma_commit(tfull_bar + 8 * a);
         if (++s == HSTAGES) { s = 0; ph ^= 1; }
         if (++a == 2) { a = 0; aph ^= 1; }
       }

@@ -1,6 +1,6 @@
 import os, sys, torch
 from functools import partial
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dvst_b200
 from dvst_b200 import _lib
 from dvst_b200.models.timesformer import VisionTransformer
