@@ -503,15 +503,17 @@ def main_ours(args):
             for F in (30, 68):
                 frames = synth_video(5, F).to(dev)
                 with torch.no_grad():
-                    score_video_device(model, frames, dl)
+                    for _ in range(2):       # warm-up with the timed call itself (workspaces, side stream, scratch)
+                        score_video_device(model, frames, dl, scorer=scorer)
                     torch.cuda.synchronize()
                     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    n_it = 8 if F == 30 else 3
                     a0.record()
-                    for _ in range(3):
+                    for _ in range(n_it):
                         score_video_device(model, frames, dl, scorer=scorer)
                     a1.record()
                     torch.cuda.synchronize()
-                aux[f"cfg3_4_3_30_F{F}_videos_per_s_per_gpu"] = 3e3 / a0.elapsed_time(a1)
+                aux[f"cfg3_4_3_30_F{F}_videos_per_s_per_gpu"] = n_it * 1e3 / a0.elapsed_time(a1)
             # the same with 8 videos per backbone pass (score_videos_device; identical losses)
             vids = [synth_video(5 + i, 30).to(dev) for i in range(8)]
             with torch.no_grad():
@@ -541,6 +543,73 @@ def main_ours(args):
                                  "dvst_select_frames; device = CUDA events around the rank's scoring, max over ranks; "
                                  "executed TFLOP/s by the de-duplicated window count of SURVEY.md section 8d")
         del model_hi
+        torch.cuda.empty_cache()
+        # ---- BASELINE configs[3]: frozen-backbone feature extraction for eval_knn (eval_knn.py:94-135): 256 clips per GPU
+        # of the 8-frame global and the 4-frame local view shapes, CLS features + indices all-gathered to rank 0 ----
+        from dvst_b200.parallel import extract_features
+        cfg4 = {}
+        for name, Tv in (("global_8f", 8), ("local_4f", 4)):
+            xs = torch.randn(256, 3, Tv, HW, HW, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+            idx = torch.arange(rank * 256, (rank + 1) * 256)
+            batches = [(xs, idx)]
+            extract_features(model, batches, 256 * world, dev)
+            sync_all()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                feats = extract_features(model, batches, 256 * world, dev)
+            c1.record()
+            sync_all()
+            tt = torch.tensor([c0.elapsed_time(c1) / 3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms4 = float(tt)
+            cfg4[name] = {"clips_per_s": 256 * world / (ms4 / 1e3), "ms_per_batch": ms4,
+                          "algorithmic_tflops_per_gpu": 256 * clip_gflop(Tv) / 1e3 / (ms4 / 1e3)}
+            if rank == 0:
+                assert feats.shape == (256 * world, 768) and bool(torch.isfinite(feats).all())
+            del xs, feats
+        cfg4["what"] = ("256 clips per GPU x (8-frame | 4-frame) x 224^2 through the frozen backbone, CLS features and sample "
+                        "indices all-gathered to rank 0 (parallel.extract_features = eval_knn.py:94-135); device-timed incl. "
+                        "the gather, max over ranks")
+        aux["cfg4_knn_feature_extraction"] = cfg4
+        torch.cuda.empty_cache()
+        # ---- BASELINE configs[4]: long clips, 32 frames (T*N = 6 272 tokens per clip): divided vs joint space-time ----
+        if rank == 0:
+            cfg5 = {}
+            for att, Bv in (("divided_space_time", 32), ("divided_space_time", 8), ("joint_space_time", 8)):
+                if att == "divided_space_time":
+                    m5 = model
+                else:
+                    m5 = VisionTransformer(img_size=224, num_classes=0, depth=12, qkv_bias=True,
+                                           norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_frames=8,
+                                           attention_type=att)
+                    m5.load_state_dict(synth_backbone_state_dict(0, depth=12, num_frames=8, attention_type=att), strict=True)
+                    m5 = m5.eval().to(dev)
+                x5 = torch.randn(Bv, 3, 32, HW, HW, generator=torch.Generator().manual_seed(11)).to(dev)
+                with torch.no_grad():
+                    m5(x5)
+                    torch.cuda.synchronize()
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record()
+                    for _ in range(3):
+                        f5 = m5(x5)
+                    c1.record()
+                    torch.cuda.synchronize()
+                ms5 = c0.elapsed_time(c1) / 3
+                gf = clip_gflop(32) if att == "divided_space_time" else 2523.6
+                cfg5[f"{att}_B{Bv}"] = {"clips_per_s": Bv / (ms5 / 1e3), "ms_per_batch": ms5,
+                                        "algorithmic_tflops": Bv * gf / 1e3 / (ms5 / 1e3)}
+                assert bool(torch.isfinite(f5).all())
+                del x5, f5
+                if m5 is not model:
+                    del m5
+            cfg5["what"] = ("32 frames x 224^2 per clip (6 272 patch tokens + CLS), ViT-B depth 12, forward only, device-resident, "
+                            "1 GPU: divided space-time (attention 3 % of the FLOPs) vs joint space-time (one 6 273-token "
+                            "attention per clip and head, 57 % of the FLOPs, flash-style tcgen05 kernel); algorithmic FLOPs "
+                            "of SURVEY.md section 8d")
+            aux["cfg5_long_clip_32f"] = cfg5
+            torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
 

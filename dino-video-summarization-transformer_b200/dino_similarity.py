@@ -207,7 +207,7 @@ class HeadScorer:
         return loss
 
 
-def _forward_windows(model, frames, starts, T, max_clips, out=None):
+def _forward_windows(model, frames, starts, T, max_clips, out=None, ws="_workspace"):
     """Features [n, 768] of the T-frame windows of `frames` [F,3,H,W] starting at `starts` (python ints, or an int32
     CUDA tensor as written by dvst_plan_windows - then nothing is copied from the host)."""
     L = _lib.lib()
@@ -226,12 +226,13 @@ def _forward_windows(model, frames, starts, T, max_clips, out=None):
     for c0 in range(0, n, max_clips):
         nb = min(max_clips, n - c0)
         need = L.dvst_workspace_bytes(model._handle, nb, T, H, W)
-        if model._workspace is None or model._workspace.numel() < need or model._workspace.device != dev:
-            model._workspace = None
-            model._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        buf = getattr(model, ws, None)
+        if buf is None or buf.numel() < need or buf.device != dev:
+            setattr(model, ws, None)
+            buf = torch.empty(need, dtype=torch.uint8, device=dev)
+            setattr(model, ws, buf)
         _lib.check(L.dvst_forward_windows(model._handle, _lib.ptr(frames), F, _lib.ptr(starts_t[c0:]), nb, T, H, W,
-                                          _lib.ptr(out[c0:]), _lib.ptr(model._workspace), model._workspace.numel(),
-                                          _lib.cur_stream()))
+                                          _lib.ptr(out[c0:]), _lib.ptr(buf), buf.numel(), _lib.cur_stream()))
     return out
 
 
@@ -273,7 +274,7 @@ def _dummy_losses(model, dev, dino_loss, scorer, local_clip_size, global_clip_si
 
 
 def score_videos_device(model, videos, dino_loss, local_clip_size=3, global_clip_size=30, scorer=None,
-                        max_rows=1 << 19):
+                        max_rows=1 << 19, small_batch_rows=150000):
     """Scores a BATCH of videos on the GPU; returns one CUDA tensor [F_v] of per-frame losses per video (no host sync).
 
     model: dvst_b200 VisionTransformer; videos: list of fp32 [F_v,3,H,W] CUDA tensors (normalised, cropped - what the
@@ -323,11 +324,31 @@ def score_videos_device(model, videos, dino_loss, local_clip_size=3, global_clip
         # window starts in units of the concatenated frame axis (windows never cross a video boundary: every start is
         # clamped to [0, F_v - T] inside its own video); built on the device, no host round trip
         s_starts, t_starts, s_idx_t, t_idx_t, groups = plan_windows(lengths, local_clip_size, global_clip_size, dev)
-        fs = _forward_windows(model, frames, s_starts, local_clip_size, max(1, max_rows // (N * local_clip_size)))
         ft = torch.empty(t_starts.numel(), model.embed_dim, dtype=torch.float32, device=dev)
-        for G, cnt, row0 in groups:
-            _forward_windows(model, frames, t_starts[row0:row0 + cnt], G, max(1, max_rows // (N * G)),
-                             out=ft[row0:row0 + cnt])
+        fs = torch.empty(s_starts.numel(), model.embed_dim, dtype=torch.float32, device=dev)
+        rows = N * (s_starts.numel() * local_clip_size + sum(G * cnt for G, cnt, _ in groups))
+        # Small batches (a single short video: ~28 three-frame student clips + one 30-frame teacher clip) leave most SMs
+        # idle and every kernel latency-bound, and the student and teacher passes are independent: run the teacher pass on
+        # a second stream with its own workspace so the two fill the machine together.  Same kernels on the same data:
+        # identical losses.  Large batches keep the single stream (nothing to gain, and one workspace).
+        overlap = rows <= small_batch_rows
+        cur = torch.cuda.current_stream()
+        if overlap:
+            if getattr(model, "_side_stream", None) is None or model._side_stream.device != dev:
+                model._side_stream = torch.cuda.Stream(device=dev)
+            side = model._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for G, cnt, row0 in groups:
+                    _forward_windows(model, frames, t_starts[row0:row0 + cnt], G, max(1, max_rows // (N * G)),
+                                     out=ft[row0:row0 + cnt], ws="_workspace_side")
+        _forward_windows(model, frames, s_starts, local_clip_size, max(1, max_rows // (N * local_clip_size)), out=fs)
+        if overlap:
+            cur.wait_stream(side)
+        else:
+            for G, cnt, row0 in groups:
+                _forward_windows(model, frames, t_starts[row0:row0 + cnt], G, max(1, max_rows // (N * G)),
+                                 out=ft[row0:row0 + cnt])
         if scorer is not None:
             loss = scorer.pair_losses(fs, ft, s_idx_t, t_idx_t)
         else:
@@ -338,12 +359,12 @@ def score_videos_device(model, videos, dino_loss, local_clip_size=3, global_clip
 
 
 def score_video_device(model, frames, dino_loss, local_clip_size=3, global_clip_size=30, scorer=None,
-                       max_rows=1 << 19):
+                       max_rows=1 << 19, **kw):
     """Scores one video on the GPU; returns the per-frame losses as a CUDA tensor [F] (no host sync).  See
     score_videos_device (this is the batch of one)."""
     if not frames.is_cuda:
         raise _lib.DvstError("dvst_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
-    return score_videos_device(model, [frames], dino_loss, local_clip_size, global_clip_size, scorer, max_rows)[0]
+    return score_videos_device(model, [frames], dino_loss, local_clip_size, global_clip_size, scorer, max_rows, **kw)[0]
 
 
 def score_video(model, frames, dino_loss=None, local_clip_size=3, global_clip_size=30, scorer=None, **kw):
