@@ -7,7 +7,8 @@ parameter containers only: `forward` packs the weights once (bf16, or bf16 hi/lo
 calls `dvst_forward_features` in csrc/libdvst.so, which runs the whole forward as hand-written sm_100a kernels on a
 resident [B,N,T,D] token layout.  There is no PyTorch / CPU fallback: a CPU input or a missing library raises.
 
-Inference only (the reference's scoring / feature-extraction callers run under torch.no_grad()).
+The reference's scoring / feature-extraction callers run under torch.no_grad(); when gradients are recorded (training a
+student) the forward still runs on the kernels and the backward is PyTorch (dvst_b200/autograd.py).
 """
 import ctypes
 import math
@@ -263,7 +264,17 @@ class VisionTransformer(nn.Module):
 
     # ------------------------------------------------------------------------------------------------------------------
     def forward_features(self, x, get_all=False, get_attn=False):
-        """[B,3,T,H,W] -> [B,768] (or [B,1+N*T,768] if get_all) - models/timesformer.py:285-345."""
+        """[B,3,T,H,W] -> [B,768] (or [B,1+N*T,768] if get_all) - models/timesformer.py:285-345.  Under torch.no_grad()
+        (every scoring / feature-extraction caller of the reference) this is the plain kernel path; when a gradient is
+        being recorded (a student being trained, train_ssl.py:483-563) the CLS-feature form goes through
+        autograd.backbone_features: same kernels forward, PyTorch recomputation backward."""
+        if torch.is_grad_enabled() and not get_all and not get_attn and x.is_cuda and \
+                (x.requires_grad or any(p.requires_grad for p in self._backbone_params())):
+            from ..autograd import backbone_features
+            return backbone_features(self, x)
+        return self._forward_features_cuda(x, get_all, get_attn)
+
+    def _forward_features_cuda(self, x, get_all=False, get_attn=False):
         if x.dim() != 5 or x.shape[1] != 3:
             raise ValueError(f"expected input [B,3,T,H,W], got {tuple(x.shape)}")
         if not x.is_cuda:

@@ -3,8 +3,8 @@
 Same constructor / forward(student_output, teacher_output, epoch) / update_center / `center` buffer as the reference.
 The cross-entropy terms run through dvst_pair_loss_indexed (one launch for all (teacher view, student view) terms),
 the batch-center column sum and the EMA are CUDA kernels, and the all-reduce in between is NCCL via torch.distributed
-exactly where the reference has it (train_ssl.py:687).  Forward only (no autograd): the SSL training loop itself is
-out of scope.
+exactly where the reference has it (train_ssl.py:687).  The value is computed by the kernels; its gradient w.r.t. the
+student output by dvst_b200/autograd.py (PyTorch).  The SSL training loop itself is out of scope.
 """
 import numpy as np
 import torch
@@ -29,8 +29,17 @@ class DINOLoss(nn.Module):
             np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),
             np.ones(nepochs - warmup_teacher_temp_epochs) * teacher_temp))
 
-    @torch.no_grad()
     def forward(self, student_output, teacher_output, epoch):
+        """train_ssl.py:626-671.  The value comes from the fused pair-loss kernel; when the student output carries a graph
+        the gradient w.r.t. it is supplied by autograd._TrainLoss (PyTorch), so `loss.backward()` works as in the
+        reference's training step (train_ssl.py:524-540)."""
+        if torch.is_grad_enabled() and student_output.requires_grad:
+            from .autograd import _TrainLoss
+            return _TrainLoss.apply(self, student_output, teacher_output, epoch)
+        return self._forward_cuda(student_output, teacher_output, epoch)
+
+    @torch.no_grad()
+    def _forward_cuda(self, student_output, teacher_output, epoch):
         if not student_output.is_cuda:
             raise _lib.DvstError("dvst_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
         L = _lib.lib()

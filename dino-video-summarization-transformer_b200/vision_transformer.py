@@ -123,6 +123,14 @@ class DINOHead(nn.Module):
         return z, zf
 
     def forward(self, x):
+        """Logits [B, out_dim] (vision_transformer.py:278-282).  With gradients recorded: kernels forward, PyTorch
+        recomputation backward (autograd.head_logits)."""
+        if torch.is_grad_enabled() and x.is_cuda and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import head_logits
+            return head_logits(self, x)
+        return self._forward_cuda(x)
+
+    def _forward_cuda(self, x):
         z, _ = self.bottleneck(x)
         pk = self._packed
         L = _lib.lib()

@@ -518,3 +518,51 @@ def test_nccl_world2_extract_features_update_center_gather_scores(dev):
                           "--master-addr", "127.0.0.1", "--master-port", "29541",
                           os.path.join(root, "tools", "nccl_check.py")], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "nccl ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_training_forward_has_a_pytorch_backward(dev):
+    """student forward through MultiCropWrapper -> DINOHead -> training DINOLoss with
+    loss.backward() (train_ssl.py:483-540).  Forward values are the kernels'; gradients come from the PyTorch
+    recomputation in dvst_b200/autograd.py and must equal torch.autograd through the oracle (fp32) on the same inputs."""
+    from dvst_b200.utils import MultiCropWrapper
+    torch.manual_seed(0)
+    sd = synth_backbone_state_dict(6, depth=2, num_frames=8)
+    hsd = synth_head_state_dict(3, out_dim=4096)
+    m = VisionTransformer(img_size=224, num_classes=0, depth=2, qkv_bias=True,
+                          norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_frames=8)
+    m.load_state_dict(sd, strict=True)
+    head = DINOHead(768, 4096)
+    head.load_state_dict(hsd, strict=True)
+    student = MultiCropWrapper(m, head).to(dev).train()
+    B = 2
+    views = [synth_clips(300 + i, B, 2, 224, 224).to(dev) for i in range(2)] + \
+            [synth_clips(310 + i, B, 2, 96, 96).to(dev) for i in range(2)]       # 2 global (224^2) + 2 local (96^2) views
+    teacher_out = torch.randn(2 * B, 4096, generator=torch.Generator().manual_seed(9)).to(dev)
+    L = TrainDINOLoss(4096, 4, 0.04, 0.07, 3, 10).to(dev)
+    c0 = L.center.clone()
+    out = student(views)
+    assert out.requires_grad and tuple(out.shape) == (4 * B, 4096)
+    loss = L(out, teacher_out, epoch=1)
+    loss.backward()
+    got = {n: p.grad.detach().cpu() for n, p in student.named_parameters() if p.grad is not None}
+    assert "backbone.blocks.0.temporal_fc.weight" in got and "head.mlp.0.weight" in got and "head.last_layer.weight_v" in got
+
+    # oracle: the same computation in fp32 torch on the CPU, differentiated by torch.autograd
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ohd = {k: v.clone().requires_grad_(k != "last_layer.weight_g") for k, v in hsd.items()}
+    feats = torch.cat([O.forward_features(osd, torch.cat([v.cpu() for v in views[:2]])),
+                       O.forward_features(osd, torch.cat([v.cpu() for v in views[2:]]))])
+    o_out = O.dino_head(ohd, feats)
+    o_loss = O.dino_train_loss(o_out, teacher_out.cpu(), c0.cpu(), float(L.teacher_temp_schedule[1]), 0.1, 4)
+    o_loss.backward()
+    assert abs(float(loss) - float(o_loss)) / float(o_loss) < 2e-3          # forward: kernels (bf16 operands) vs fp32
+    worst = 0.0
+    for k, v in osd.items():
+        g = got["backbone." + k]
+        worst = max(worst, ((g - v.grad).norm() / (v.grad.norm() + 1e-12)).item())
+    for k, v in ohd.items():
+        if v.requires_grad:
+            g = got["head." + k]
+            worst = max(worst, ((g - v.grad).norm() / (v.grad.norm() + 1e-12)).item())
+    # the backward runs on the kernels' student output (bf16-level forward difference feeds softmax(s / tau)): a few 1e-3
+    assert worst < 2e-2, worst
