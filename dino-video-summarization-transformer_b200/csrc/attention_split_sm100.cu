@@ -63,6 +63,33 @@ __device__ long long dvst_sp2_trace[4 * 8 * 4];   // [role: mma, softmax w4, sof
 #define SP2_TR(role, ev) do {} while (0)
 #endif
 
+// exp2 on the FMA pipe for a fixed subset of the score pairs (the FlashAttention-4 arrangement): the softmax is bound by
+// the MUFU (16 ex2 / clk / SM, ~14 reachable - tools/tmem_bench.cu), while the FMA pipe idles.  Cody-Waite: n = round(x)
+// through the 1.5 * 2^23 magic constant, f = x - n in [-0.5, 0.5], 2^f by a cubic (max relative error 1.4e-4 in fp32,
+// 30x below the bf16 rounding of P), result = 2^f with n added into the exponent field.  x is clamped to [-126, 127]: below
+// the result would leave the normal range, above it must stay huge so that the row still reaches the fix-up kernel.
+// Measured (cfg2 launch, same box): 6 of 16 pairs on the FMA pipe (mask 0x5252) 0.2415 -> 0.2518 ms - the two clamps and the
+// exponent insertion are ALU-pipe instructions, and the ALU pipe (bf16 packing, masks) is already ~48 % busy, so the
+// exponentials saved on the MUFU are paid back there.  Left switched off (mask 0); packed ex2.approx.f16x2 / bf16x2 are no way
+// out either: they compile to TWO MUFU.EX2 (one per half) and run at the same 13.5 exp / clk / SM.
+constexpr uint32_t SP2_POLY_PAIRS = 0x0000u;   // bit j: pair j (of 16 per 32-column chunk) is computed on the FMA pipe
+__device__ __forceinline__ void exp2_poly2(float& a0, float& a1) {
+  a0 = fminf(fmaxf(a0, -126.0f), 127.0f);
+  a1 = fminf(fmaxf(a1, -126.0f), 127.0f);
+  const uint64_t x2 = pk2(a0, a1);
+  const uint64_t magic = 0x4B4000004B400000ull, nmagic = 0xCB400000CB400000ull, mone = 0xBF800000BF800000ull;
+  const uint64_t t2 = add2(x2, magic);
+  const uint64_t f2 = fma2(add2(t2, nmagic), mone, x2);
+  uint64_t p2 = fma2(0x3D61FB263D61FB26ull, f2, 0x3E786ECB3E786ECBull);
+  p2 = fma2(p2, f2, 0x3F31798D3F31798Dull);
+  p2 = fma2(p2, f2, 0x3F7FFB4A3F7FFB4Aull);
+  float p0, p1, t0, t1;
+  unpk2(p2, p0, p1);
+  unpk2(t2, t0, t1);
+  a0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  a1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
 struct Sp2Geom {
   int K0;      // keys of the first half (multiple of 16); the second half holds NPAD - K0
   int p1_col;  // TMEM column (inside the region) of the second half's P
@@ -346,7 +373,13 @@ spatial_attention_split_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, c
             if (2 * j < ncols) {
               float a0, a1;
               unpk2(fma2(pk2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), scale2, nmoff2), a0, a1);
-              float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+              float e0, e1;
+              if ((SP2_POLY_PAIRS >> j) & 1u) {
+                e0 = a0; e1 = a1;
+                exp2_poly2(e0, e1);
+              } else {
+                e0 = ex2_approx(a0); e1 = ex2_approx(a1);
+              }
               if (masked) {
                 if (col + 2 * j >= S) e0 = 0.f;
                 if (col + 2 * j + 1 >= S) e1 = 0.f;

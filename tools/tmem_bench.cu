@@ -81,6 +81,46 @@ __global__ void __launch_bounds__(256, 1) bench(int mode, int iters, long long* 
       tmem_ld_32x32(base + col, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) xs[j] += ex2a(__uint_as_float(v2[j]) * 1e-30f);
+    } else if (mode == 8) {
+      // packed half-precision exponentials: 16 x ex2.approx.f16x2 = 32 exponentials per iteration
+      uint32_t* hx = reinterpret_cast<uint32_t*>(xs);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        uint32_t r;
+        asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(hx[j]));
+        hx[j] = r ^ 0x80008000u;   // keep the values bounded: alternate the sign
+      }
+    } else if (mode == 9) {
+      uint32_t* hx = reinterpret_cast<uint32_t*>(xs);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        uint32_t r;
+        asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(hx[j]));
+        hx[j] = r ^ 0x80008000u;
+      }
+    } else if (mode == 10) {
+      // FMA-pipe exp2 (Cody-Waite + cubic, packed fp32x2): 32 exponentials per iteration
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        uint64_t x2, r2;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(xs[2 * j]), "f"(xs[2 * j + 1]));
+        // n = round(x) via the magic constant, f = x - n in [-0.5, 0.5]
+        const uint64_t magic = 0x4B4000004B400000ull;   // 12582912.0f twice
+        uint64_t t2, f2;
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(x2), "l"(magic));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f2) : "l"(t2), "l"(magic));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f2) : "l"(x2), "l"(f2));
+        const uint64_t c3 = 0x3D6359A43D6359A4ull, c2 = 0x3E75FDF03E75FDF0ull, c1 = 0x3F3172183F317218ull, c0 = 0x3F8000003F800000ull;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r2) : "l"(c3), "l"(f2), "l"(c2));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r2) : "l"(r2), "l"(f2), "l"(c1));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r2) : "l"(r2), "l"(f2), "l"(c0));
+        uint32_t lo, hi, tl, th;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(r2));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(tl), "=r"(th) : "l"(t2));
+        lo += tl << 23; hi += th << 23;
+        xs[2 * j] = __uint_as_float(lo) * 1e-3f - 1.0f;
+        xs[2 * j + 1] = __uint_as_float(hi) * 1e-3f - 1.0f;
+      }
     } else {
       // x16 loads
       uint32_t w[16];
@@ -107,10 +147,11 @@ int main() {
   long long* d_c; float* d_s;
   cudaMalloc(&d_c, 8); cudaMalloc(&d_s, 4096);
   const char* names[] = {"ld.x32 + wait", "2 x ld.x32 in flight", "st.x16 + wait", "32 x ex2", "ld.x32 + 32 ex2",
-                         "ld.x32 + 32 ex2 + pack + st.x16", "pipelined ld.x32 | 32 ex2", "ld.x16 + wait"};
+                         "ld.x32 + 32 ex2 + pack + st.x16", "pipelined ld.x32 | 32 ex2", "ld.x16 + wait", "16 x ex2.f16x2 (32 exp)", "16 x ex2.bf16x2 (32 exp)",
+                         "32 x FMA-pipe exp2 (packed)"};
   const int iters = 4096;
   for (int warps = 1; warps <= 8; warps *= 2) {
-    for (int mode = 0; mode < 8; ++mode) {
+    for (int mode = 0; mode < 11; ++mode) {
       bench<<<1, warps * 32, 0>>>(mode, iters, d_c, d_s);  // warm
       bench<<<1, warps * 32, 0>>>(mode, iters, d_c, d_s);
       long long c = 0;
@@ -124,7 +165,7 @@ int main() {
       if (mode == 2) bytes = 32.0 * 16 * 4;
       if (mode == 5) bytes = 32.0 * 32 * 4;
       printf("warps %d  %-34s %8.1f clk/iter/warp   TMEM %7.1f B/clk/SM   ex2 %6.2f /clk/SM  (%s)\n", warps, names[mode], per,
-             bytes * warps / per, (mode >= 3 && mode <= 6 ? 32.0 * 32 * warps / per : 0.0), cudaGetErrorString(e));
+             bytes * warps / per, ((mode >= 3 && mode <= 6) || mode >= 8 ? 32.0 * 32 * warps / per : 0.0), cudaGetErrorString(e));
     }
   }
   return 0;
