@@ -55,7 +55,7 @@ print("\n".join(out[:14]))
 
 big = [k for k in per.values() if "gemm_bf16_tn_kernel<2" in k["name"].replace("(int)", "")]
 if big:
-    dv = [k for k in per.values() if "dvst" in k["name"]]
+    dv = [k for k in per.values() if "dvst" in k["name"]] or list(per.values())   # (-k regex:dvst captures list only ours)
     # the K = 768 deferred-LayerNorm producers (<2, 3, 0, 0> reading < 1.4 GB: A 308 MB + residual 616 MB) are HBM-bound and
     # reported separately from the tensor-bound launches (bench.py: roofline vs roofline_hbm_gemm)
     def is_hbm(k):
