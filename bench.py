@@ -536,6 +536,22 @@ def main_ours(args):
         model_hi = model_hi.eval().to(dev)
         n_r = max(4, args.msvd_videos // 3) * world
         aux["cfg3_msvd_modeR_high"] = cfg3_msvd_leg(torch, dist, model_hi, dl, None, msvd_lengths(n_r), world, rank, dev)
+        if rank == 0:
+            # the cfg2 step in precision="high" (2-term bf16 split in every GEMM and both attentions): what reference-exact
+            # mode-R scoring costs next to the bf16 step
+            xh = torch.randn(B_PER_GPU, 3, T, HW, HW, generator=torch.Generator().manual_seed(3)).to(dev)
+            with torch.no_grad():
+                model_hi(xh)
+                torch.cuda.synchronize()
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record()
+                for _ in range(3):
+                    fh = model_hi(xh)
+                    dl.pair_losses(fh, fh, s_idx, t_idx)
+                h1.record()
+                torch.cuda.synchronize()
+            aux["precision_high_ms_per_step"] = h0.elapsed_time(h1) / 3
+            del xh, fh
         aux["cfg3_msvd_note"] = ("MSVD-shaped = video lengths at evenly spaced quantiles of the 1 970 list lengths of the "
                                  "reference's loss_msvd_4_3_30.json; weak scaling (videos per GPU fixed), LPT sharding "
                                  "(parallel.shard_videos); e2e = uint8 frames from pinned host memory -> H2D -> "

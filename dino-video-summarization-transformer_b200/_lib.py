@@ -74,6 +74,8 @@ SIGNATURES = {
     "dvst_attention_scratch_bytes": (c_ll, [c_int, c_int, c_int]),
     "dvst_attention_ws": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p,
                                   c_ll, c_void_p]),
+    "dvst_attention_hp": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p,
+                                  c_ll, c_void_p]),
     "dvst_attention": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p]),
 }
 

@@ -151,6 +151,13 @@ int dvst_attention(const void* qkv, long long ld, void* out, long long ldo, floa
   return launch_attention(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, 0, static_cast<cudaStream_t>(stream));
 }
 
+int dvst_attention_hp(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                      int N, long long cls_base, void* scratch, long long scratch_bytes, void* stream) {
+  if (ld < 6 * 768 || ldo < 2 * 768) return set_error("dvst_attention_hp: rows must hold the [hi | lo] pairs (ld >= 4608, ldo >= 1536)");
+  return launch_attention(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, 1, static_cast<cudaStream_t>(stream),
+                          scratch, scratch_bytes);
+}
+
 long long dvst_attention_scratch_bytes(int B, int T, int N) {
   return (B > 0 && T > 0 && N > 0) ? spatial_attention_scratch_bytes(B, T, N) : 0;
 }

@@ -747,6 +747,13 @@ int launch_attention(const void* qkv, long long ld, void* out, long long ldo, fl
     if (rc != 1) return rc;
     rc = 0;
   }
+  if (split && (mode == 1 || mode == 3) && attention_impl() == 1) {
+    // precision = "high": hi / lo operands on tcgen05 (attention_hp_sm100.cu)
+    rc = launch_spatial_attention_hp_sm100(qkv, ld, out, ldo, cls_out, mode, B, T, N, cls_base, st, scratch, scratch_bytes);
+    if (rc == 0) { count_launch(); return 0; }
+    if (rc != 1) return rc;
+    rc = 0;
+  }
   if (!split && mode == 2) {
     // joint space-time attention: flash-style tcgen05 kernel (attention_sm100.cu)
     rc = launch_joint_attention_sm100(qkv, ld, out, ldo, B, N * T, cls_base, st);

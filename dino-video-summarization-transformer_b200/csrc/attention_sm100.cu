@@ -449,6 +449,7 @@ __global__ void __launch_bounds__(128) attention_fixup_kernel(const SpParams p) 
 // for 32 <= NPAD <= 208)
 static int g_attention_impl = 1;
 void set_attention_impl(int impl) { g_attention_impl = impl == 0 ? 0 : (impl == 2 ? 2 : (impl == 3 ? 3 : 1)); }
+int attention_impl() { return g_attention_impl; }
 int launch_spatial_attention_split_sm100(const SpParams& p, const CUtensorMap& tmIn, const CUtensorMap& tmOutA,
                                          const CUtensorMap& tmOutB, int grid, cudaStream_t st);
 

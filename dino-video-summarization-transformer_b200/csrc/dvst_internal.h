@@ -118,6 +118,12 @@ int launch_joint_attention_sm100(const void* qkv, long long ld, void* out, long 
 // 1 (default) tcgen05: split kernel (attention_split_sm100.cu) where it applies, else first generation, one-pass softmax
 // when scratch is given; 3 first generation one-pass; 2 first generation two-pass; 0 mma.sync
 void set_attention_impl(int impl);
+int attention_impl();
+// split-precision (bf16 hi / lo operands) spatial attention on tcgen05 (attention_hp_sm100.cu): same return codes; needs the
+// scratch of the one-pass softmax
+int launch_spatial_attention_hp_sm100(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode,
+                                      int B, int T, int N, long long cls_base, cudaStream_t st, void* scratch,
+                                      long long scratch_bytes);
 
 int launch_select_frames(const double* loss, long long ld, const int* n_loss, const int* n_unsampled, int V, int rate,
                          int N, int* out, cudaStream_t st);

@@ -190,6 +190,14 @@ long long dvst_attention_scratch_bytes(int B, int T, int N);
 int dvst_attention_ws(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
                       int N, long long cls_base, void* scratch, long long scratch_bytes, void* stream);
 
+/* Split-precision form (precision = "high"): every operand is a bf16 [hi | lo] pair - qkv rows [q k v hi (2304) | q k v lo
+ * (2304)] (ld >= 4608), out rows [hi (768) | lo (768)] (ldo >= 1536), lo = bf16(x - float(hi)) - and every product is
+ * evaluated as hi*hi + hi*lo + lo*hi (~16 mantissa bits end to end; what reference-exact mode-R scoring needs).  Modes 1 / 3
+ * with scratch and at most 208 key columns run the tcgen05 kernel of csrc/attention_hp_sm100.cu, everything else the
+ * mma.sync split kernels.  cls_out (mode 1) stays fp32. */
+int dvst_attention_hp(const void* qkv, long long ld, void* out, long long ldo, float* cls_out, int mode, int B, int T,
+                      int N, long long cls_base, void* scratch, long long scratch_bytes, void* stream);
+
 /* Adaptive frame selection for a batch of videos (datasets_custom/frame_selection_loader.py:115-172) on the device, in
  * the reference's fp64 arithmetic (numpy pairwise sum, sequential cumsum, first-minimum argmin): identical index lists.
  *   loss        fp64 [n_videos, ld] device: per-sampled-frame losses of video v in row v (the JSON values; fp32 scores

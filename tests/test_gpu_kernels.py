@@ -501,3 +501,45 @@ def test_joint_attention_rescale_path(dev):
         ref[r] = _attn_ref(q[r], k[r], v[r])
     assert torch.isfinite(out.float()).all()
     assert _rel(out.float(), ref) < 5e-3
+
+
+@pytest.mark.parametrize("mode,B,T,N,impl", [(1, 2, 3, 196, 1), (3, 2, 2, 196, 1), (1, 2, 3, 36, 1), (1, 3, 2, 100, 1),
+                                              (1, 2, 2, 196, 0), (1, 9, 16, 196, 1)])
+def test_attention_high_precision_tcgen05(dev, mode, B, T, N, impl):
+    """Split-precision spatial attention (bf16 hi / lo operands, hi*hi + hi*lo + lo*hi on tcgen05, P written as a hi / lo
+    pair; csrc/attention_hp_sm100.cu) against fp64 torch on the same operands: ~16 mantissa bits end to end.  impl 0 =
+    the mma.sync split kernel it replaces.  (9, 16, 196): 1 728 problems, 11 - 12 per CTA (barrier phases wrap many times)."""
+    torch.manual_seed(11 + mode + N)
+    L = _lib.lib()
+    Mt = B * N * T
+    ncls = B * T if mode == 3 else B
+    x = torch.randn(Mt + ncls, 2304, device=dev) * 1.5
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    qkv = torch.cat([hi, lo], 1).contiguous()                       # [rows, 4608]
+    xe = hi.double() + lo.double()                                  # what the kernel's operands represent
+    nb = L.dvst_attention_scratch_bytes(B, T, N)
+    scratch = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    out = torch.zeros(Mt + ncls, 1536, device=dev, dtype=torch.bfloat16)
+    cls_out = torch.zeros(B, T, 768, device=dev)
+    try:
+        L.dvst_set_attention_impl(impl)
+        _lib.check(L.dvst_attention_hp(_lib.ptr(qkv), 4608, _lib.ptr(out), 1536, _lib.ptr(cls_out), mode, B, T, N, Mt,
+                                       _lib.ptr(scratch), nb, _lib.cur_stream()))
+    finally:
+        L.dvst_set_attention_impl(1)
+    torch.cuda.synchronize()
+    got_all = out[:, :768].double() + out[:, 768:].double()
+    rows = torch.arange(Mt, device=dev).reshape(B, N, T)
+    worst = 0.0
+    for bb in range(min(B, 3)):
+        for t in range(T if T <= 3 else 2):
+            c = Mt + (bb * T + t if mode == 3 else bb)
+            r = torch.cat([rows[bb, :, t], torch.tensor([c], device=dev)])
+            for h in (0, 5, 11):
+                q, k, v = [xe[r, i * 768 + h * 64: i * 768 + h * 64 + 64] for i in range(3)]
+                ref = torch.softmax(q @ k.T * 0.125, -1) @ v
+                cls = cls_out[bb, t, h * 64:h * 64 + 64].double() if mode == 1 else got_all[c, h * 64:h * 64 + 64]
+                got = torch.cat([got_all[r[:-1], h * 64:h * 64 + 64], cls[None]])
+                worst = max(worst, ((got - ref).norm() / ref.norm()).item())
+    assert worst < 1e-4, worst
