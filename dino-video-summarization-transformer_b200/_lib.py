@@ -32,6 +32,9 @@ SIGNATURES = {
     "dvst_set_attention_impl": (None, [c_int]),
     "dvst_set_chunk_rows": (None, [c_ll]),
     "dvst_set_ln_fusion": (None, [c_int]),
+    "dvst_set_temporal_fusion": (None, [c_int]),
+    "dvst_gemm_ln_temporal_attention": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_ll,
+                                                c_int, c_void_p, c_ll, c_void_p]),
     "dvst_profile_enable": (None, [c_int]),
     "dvst_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "dvst_create": (c_int, [c_void_p, c_void_p]),
@@ -97,6 +100,9 @@ def lib():
         # experiment switches (A/B runs of bench.py on one box): DVST_LN_FUSION=0 forces the stand-alone LayerNorm
         if os.environ.get("DVST_LN_FUSION") == "0":
             l.dvst_set_ln_fusion(0)
+        # DVST_TATTN_FUSION=0: qkv GEMM + temporal attention as two kernels (the round-1 form)
+        if os.environ.get("DVST_TATTN_FUSION") == "0":
+            l.dvst_set_temporal_fusion(0)
         # DVST_ATTENTION_IMPL: 1 default (split tcgen05 kernel), 3 first-generation one-pass, 2 two-pass, 0 mma.sync
         if os.environ.get("DVST_ATTENTION_IMPL"):
             l.dvst_set_attention_impl(int(os.environ["DVST_ATTENTION_IMPL"]))

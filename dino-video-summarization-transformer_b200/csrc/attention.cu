@@ -13,10 +13,13 @@
 // Math runs on mma.sync m16n8k16 bf16 (fp32 accumulate); attention is ~3.4 % of the path's FLOPs.
 #include "dvst_internal.h"
 #include "ptx.cuh"
+#include "mma_sync.cuh"
 
 namespace dvst {
 
 namespace {
+
+using namespace mma;
 
 constexpr int HD = 64;     // head dim
 constexpr int DMODEL = 768;
@@ -50,35 +53,10 @@ __device__ __forceinline__ long long row_of(const AttnParams& p, int seq, int i)
   }
 }
 
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
 // bf16x2 rounding residual of (a, b) given their packed bf16 rounding `hi`
 __device__ __forceinline__ uint32_t pack_lo2(float a, float b, uint32_t hi) {
   const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hi);
   return pack2(a - __low2float(hb), b - __high2float(hb));
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");

@@ -62,6 +62,16 @@ struct GemmArgs {
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 void set_gemm_cta_group(int cg);  // 1 or 2 (default 2); tuning / test hook
 
+// Temporal half of a divided block in one kernel (gemm_tattn_sm100.cu): deferred-LayerNorm qkv GEMM whose epilogue runs the
+// temporal attention out of shared memory; the packed qkv tensor is never written.  w / bias / colsum are HEAD-PERMUTED
+// (row 192 h + 64 part + d = original row 768 part + 64 h + d).  Returns 0 when it ran, -1 when T is not covered (T > 64:
+// callers run the qkv GEMM + temporal attention kernels), DVST_ERR (1) on error.
+int launch_gemm_ln_tattn(const void* xb, long long ldxb, const void* w_perm, const float* bias_perm,
+                         const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T, void* out,
+                         long long ldo, cudaStream_t stream);
+void set_temporal_fusion(int on);  // 1 (default) use the fused kernel where the permuted tensors are registered
+int temporal_fusion();
+
 int launch_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out,
                         long long ldo, int out_kind, long long lo_off, long long M, float eps, cudaStream_t st,
                         long long rm_group = 0, long long rm_stride = 0, long long rm_offset = 0);

@@ -155,20 +155,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-
 // kOut: 0 = bf16, 1 = fp32 (plain or reduce-add), 2 = bf16 hi/lo pair.  kAct: 0 = none, 1 = exact-erf GELU.  Compile-time
 // so the epilogue (issue-bound next to the 256x256x768 MMA of fc1) carries no predicated code of the other modes.
 // kOut = 3: fp32 in-place residual (TMA load + add + TMA store) + bf16 copy + row statistics (deferred LayerNorm producer).

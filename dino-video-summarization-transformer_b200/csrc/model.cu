@@ -39,6 +39,9 @@ struct BlockW {
   const void *tqkv_wf = nullptr, *qkv_wf = nullptr, *fc1_wf = nullptr;
   const float *tqkv_sf = nullptr, *tqkv_bf = nullptr, *qkv_sf = nullptr, *qkv_bf = nullptr, *fc1_sf = nullptr,
               *fc1_bf = nullptr;
+  // head-permuted copies of the folded temporal qkv tensors (optional): the fused qkv GEMM + temporal attention kernel
+  const void* tqkv_wfp = nullptr;
+  const float *tqkv_sfp = nullptr, *tqkv_bfp = nullptr;
 };
 
 struct Model {
@@ -46,6 +49,7 @@ struct Model {
   std::unordered_map<std::string, const void*> named;
   bool finalized = false;
   bool fused_ln = false;  // every block carries the folded tensors
+  bool fused_tattn = false;  // ... and the head-permuted temporal qkv tensors (gemm_tattn_sm100.cu)
   const void* pe_w = nullptr;
   const float *pe_b = nullptr, *cls_pos0 = nullptr, *pos = nullptr, *time_embed = nullptr, *norm_w = nullptr,
               *norm_b = nullptr;
@@ -173,6 +177,7 @@ int dvst_finalize_weights(dvst_model* h) {
     return it == m->named.end() ? nullptr : it->second;
   };
   bool all = m->cfg.precision == DVST_PRECISION_BF16;
+  bool all_perm = divided;
   for (int i = 0; i < m->cfg.depth; ++i) {
     const std::string p = "blocks." + std::to_string(i) + ".";
     BlockW& b = m->blocks[i];
@@ -181,6 +186,10 @@ int dvst_finalize_weights(dvst_model* h) {
       b.tqkv_sf = static_cast<const float*>(opt(p + "temporal_attn.qkv.sf"));
       b.tqkv_bf = static_cast<const float*>(opt(p + "temporal_attn.qkv.bf"));
       all = all && b.tqkv_wf && b.tqkv_sf && b.tqkv_bf;
+      b.tqkv_wfp = opt(p + "temporal_attn.qkv.wfp");
+      b.tqkv_sfp = static_cast<const float*>(opt(p + "temporal_attn.qkv.sfp"));
+      b.tqkv_bfp = static_cast<const float*>(opt(p + "temporal_attn.qkv.bfp"));
+      all_perm = all_perm && b.tqkv_wfp && b.tqkv_sfp && b.tqkv_bfp;
     }
     b.qkv_wf = opt(p + "attn.qkv.wf");
     b.qkv_sf = static_cast<const float*>(opt(p + "attn.qkv.sf"));
@@ -191,6 +200,7 @@ int dvst_finalize_weights(dvst_model* h) {
     all = all && b.qkv_wf && b.qkv_sf && b.qkv_bf && b.fc1_wf && b.fc1_sf && b.fc1_bf;
   }
   m->fused_ln = all;
+  m->fused_tattn = all && all_perm;
   m->finalized = true;
   return 0;
 }
@@ -199,6 +209,7 @@ int dvst_finalize_weights(dvst_model* h) {
 // (x, a, qkv, hid) stay resident in the 126 MB L2 between producer and consumer kernels; 0 = whole batch in one pass.
 static int g_ln_fusion = 1;
 void dvst_set_ln_fusion(int on) { g_ln_fusion = on != 0 ? 1 : 0; }
+void dvst_set_temporal_fusion(int on) { set_temporal_fusion(on); }
 static long long g_chunk_rows = 0;
 void dvst_set_chunk_rows(long long rows) { g_chunk_rows = rows < 0 ? 0 : rows; }
 static int chunk_clips(int B, long long rows_per_clip) {
@@ -345,13 +356,22 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
     const BlockW& b = m->blocks[i];
     if (att == DVST_ATTN_DIVIDED) {
       // temporal attention over the T tokens of every (b, n); CLS rows excluded (:127-135)
-      if (fl) {
-        DVST_TRY(gemm_ln(b.tqkv_wf, b.tqkv_sf, b.tqkv_bf, 0, Mt, 3 * D, w.qkv, ldq, 0));
-      } else {
-        DVST_TRY(ln(w.x, b.tnorm_w, b.tnorm_b, Mt));
-        DVST_TRY(gemm(w.a, lda, b.tqkv_w, b.tqkv_b, Mt, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
+      // bf16 + deferred LayerNorm + T <= 64: qkv GEMM and temporal attention are ONE kernel, the qkv tensor stays in shared
+      // memory (gemm_tattn_sm100.cu); the choice depends on the model and T only, never on the batch
+      int fused = -1;
+      if (fl && m->fused_tattn && temporal_fusion()) {
+        fused = launch_gemm_ln_tattn(xb, D, b.tqkv_wfp, b.tqkv_bfp, b.tqkv_sfp, w.stats, LN_EPS, Mt, T, w.a, lda, st);
+        if (fused > 0) return fused;
       }
-      DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, nullptr, 0, B, T, static_cast<int>(N), Mt, split, st));
+      if (fused != 0) {
+        if (fl) {
+          DVST_TRY(gemm_ln(b.tqkv_wf, b.tqkv_sf, b.tqkv_bf, 0, Mt, 3 * D, w.qkv, ldq, 0));
+        } else {
+          DVST_TRY(ln(w.x, b.tnorm_w, b.tnorm_b, Mt));
+          DVST_TRY(gemm(w.a, lda, b.tqkv_w, b.tqkv_b, Mt, 3 * D, D, nullptr, w.qkv, ldq, act_kind, 0));
+        }
+        DVST_TRY(launch_attention(w.qkv, ldq, w.a, lda, nullptr, 0, B, T, static_cast<int>(N), Mt, split, st));
+      }
       // temporal_fc(proj(.)) folded into one 768x768 GEMM at pack time; residual add fused (:131-135)
       if (fl) DVST_TRY(gemm_res(w.a, b.tproj_w, b.tproj_b, 0, Mt, D));
       else DVST_TRY(gemm(w.a, lda, b.tproj_w, b.tproj_b, Mt, D, D, w.x, w.x, D, 1, 0));

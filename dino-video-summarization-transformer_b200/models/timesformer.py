@@ -239,10 +239,15 @@ class VisionTransformer(nn.Module):
                 pk[name + ".wf"] = wf
                 pk[name + ".sf"] = wf.double().sum(1).float().contiguous()
                 pk[name + ".bf"] = (lin.bias.detach().to(device).double() + W @ beta).float().contiguous()
+            # head-major row order of the temporal qkv tensors for the fused qkv-GEMM + temporal-attention kernel
+            # (csrc/gemm_tattn_sm100.cu): one 192-row block per head = [q_h | k_h | v_h]
+            hp = torch.arange(2304, device=device).view(3, 12, 64).permute(1, 0, 2).reshape(-1)
             for i, blk in enumerate(self.blocks):
                 p = f"blocks.{i}."
                 if self.attention_type == 'divided_space_time':
                     fold(blk.temporal_attn.qkv, blk.temporal_norm1, p + "temporal_attn.qkv")
+                    for sfx in ("wf", "sf", "bf"):
+                        pk[p + "temporal_attn.qkv." + sfx + "p"] = pk[p + "temporal_attn.qkv." + sfx][hp].contiguous()
                 fold(blk.attn.qkv, blk.norm1, p + "attn.qkv")
                 fold(blk.mlp.fc1, blk.norm2, p + "mlp.fc1")
         P = int(round(math.sqrt(self.pos_embed.shape[1] - 1)))

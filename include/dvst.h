@@ -55,6 +55,11 @@ void dvst_set_attention_impl(int impl);
  * LayerNorm path (see dvst_gemm_bf16_ln); 0 forces the stand-alone LayerNorm kernel.  Call before dvst_workspace_bytes. */
 void dvst_set_ln_fusion(int on);
 
+/* Tuning / test hook: 1 (default) runs the temporal half of a divided block (temporal_norm1 -> qkv -> attention) as ONE
+ * kernel when the head-permuted folded tensors are registered (see dvst_gemm_ln_temporal_attention); 0 runs the qkv GEMM
+ * and the temporal attention kernel separately.  For T in {16, 32, 64} both forms give the same bits. */
+void dvst_set_temporal_fusion(int on);
+
 /* L2-residency tuning: walk a batch in chunks of about `rows` token rows (0 = whole batch per pass).  Results are
  * bit-identical for any value (rows of every kernel are independent).  Call before dvst_workspace_bytes. */
 void dvst_set_chunk_rows(long long rows);
@@ -79,7 +84,10 @@ void dvst_destroy(dvst_model* m);
  *   blocks.<i>.attn.proj.{w,b}, blocks.<i>.mlp.fc1.{w [3072,768*k], b}, blocks.<i>.mlp.fc2.{w [768,3072*k], b}
  * Optional (bf16 precision; all of them or none): the deferred-LayerNorm form of the three Linears that follow a norm,
  *   blocks.<i>.{temporal_attn.qkv,attn.qkv,mlp.fc1}.wf bf16 [N, 768] = bf16(gamma * W), .sf fp32 [N] = row sums of wf,
- *   .bf fp32 [N] = b + W beta   (gamma / beta of temporal_norm1 / norm1 / norm2 respectively)                       */
+ *   .bf fp32 [N] = b + W beta   (gamma / beta of temporal_norm1 / norm1 / norm2 respectively)
+ * Optional on top of those: blocks.<i>.temporal_attn.qkv.{wfp,sfp,bfp} = the same three tensors with their 2304 rows
+ *   permuted head-major (row 192 h + 64 part + d <- row 768 part + 64 h + d, part = q, k, v): enables the fused
+ *   qkv-GEMM + temporal-attention kernel.                                                                               */
 int dvst_set_weight(dvst_model* m, const char* name, const void* dev_ptr);
 int dvst_finalize_weights(dvst_model* m);
 
@@ -174,6 +182,16 @@ int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw
                       const float* ln_stats, const float* ln_colsum, float ln_eps, float* x_inout, long long ldx,
                       void* xb, long long ldxb, float* stats_out, const float* xoff, void* out, long long ldo, int act,
                       void* stream);
+/* temporal_norm1 -> temporal_attn.qkv -> softmax(q k^T / 8) v of temporal_attn, heads concatenated
+ * (models/timesformer.py:127-131 with Attention.forward :68-81, up to but not including temporal_attn.proj) in one kernel:
+ * the deferred-LayerNorm consumer GEMM above with N = 2304, whose epilogue keeps q | k | v of a (128-row, one-head) tile in
+ * shared memory and runs the temporal attention from there - the packed qkv tensor is never written.
+ *   xb, ln_stats : as for the consumer form; M rows = whole sequences of T consecutive rows ((b, n, t) order), 1 <= T <= 64
+ *   w_perm bf16 [2304, 768], bias_perm / colsum_perm fp32 [2304]: head-permuted (row 192 h + 64 part + d)
+ *   out bf16 [M, ldo]: attention output, head h in columns [64 h, 64 h + 64) - the A operand of the proj GEMM. */
+int dvst_gemm_ln_temporal_attention(const void* xb, long long ldxb, const void* w_perm, const float* bias_perm,
+                                    const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T,
+                                    void* out, long long ldo, void* stream);
 /* nn.LayerNorm(768, eps) over M rows of fp32 (models/timesformer.py:99,105,112,245).  out_kind as above. */
 int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,
                       int out_kind, long long lo_off, long long M, float eps, void* stream);

@@ -543,3 +543,64 @@ def test_attention_high_precision_tcgen05(dev, mode, B, T, N, impl):
                 got = torch.cat([got_all[r[:-1], h * 64:h * 64 + 64], cls[None]])
                 worst = max(worst, ((got - ref).norm() / ref.norm()).item())
     assert worst < 1e-4, worst
+
+
+# ---- temporal half of a divided block in one kernel: deferred-LayerNorm qkv GEMM + temporal attention out of shared memory
+@pytest.mark.parametrize("T,n_seq", [(16, 313), (16, 8), (32, 77), (64, 9), (8, 401), (4, 1000), (1, 300), (30, 131),
+                                     (3, 1571), (5, 52), (17, 40), (48, 7), (2, 64)])
+def test_fused_temporal_qkv_attention(dev, T, n_seq):
+    """dvst_gemm_ln_temporal_attention vs the two-kernel form (dvst_gemm_bf16_ln consumer -> dvst_attention mode 0) and vs
+    an fp64 torch statement of temporal_norm1 -> qkv -> softmax(q k^T / 8) v (models/timesformer.py:127-131, :68-81).
+    Tile tails (M not a multiple of the 2 x R tile), sequences that straddle 16-row query tiles (T = 30, 3, 5, 17) and
+    one-sequence tiles (T = 48) are covered."""
+    torch.manual_seed(T * 1000 + n_seq)
+    L = _lib.lib()
+    M = T * n_seq
+    x = torch.randn(M, 768, device=dev) * 1.7 + 0.2
+    x[:, 5] += 9.0
+    gamma = torch.randn(768, device=dev) * 0.1 + 1.0
+    beta = torch.randn(768, device=dev) * 0.1
+    W = torch.randn(2304, 768, device=dev) * 0.06
+    b = torch.randn(2304, device=dev) * 0.1
+    xb = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+    stats = torch.empty(M, 6, 2, device=dev)
+    xoff = torch.empty(M, device=dev)
+    _lib.check(L.dvst_rowstats768(_lib.ptr(x), 768, _lib.ptr(xb), 768, _lib.ptr(stats), _lib.ptr(xoff), M,
+                                  _lib.cur_stream()))
+    # two kernels: packed qkv in HBM, then the temporal attention kernel
+    qkv = _ln_consumer(xb, stats, W, b, gamma, beta, 0)
+    two = torch.full((M, 768), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(L.dvst_attention(_lib.ptr(qkv), 2304, _lib.ptr(two), 768, None, 0, n_seq, T, 1, M, _lib.cur_stream()))
+    # one kernel, head-permuted folded tensors
+    wf = (W.double() * gamma.double()[None, :]).float().bfloat16().contiguous()
+    sf = wf.double().sum(1).float().contiguous()
+    bf = (b.double() + W.double() @ beta.double()).float().contiguous()
+    hp = torch.arange(2304, device=dev).view(3, 12, 64).permute(1, 0, 2).reshape(-1)
+    wfp, sfp, bfp = wf[hp].contiguous(), sf[hp].contiguous(), bf[hp].contiguous()
+    guard = 64
+    buf = torch.full((M + guard, 768), 7.0, device=dev, dtype=torch.bfloat16)   # rows past M must stay untouched
+    _lib.check(L.dvst_gemm_ln_temporal_attention(_lib.ptr(xb), 768, _lib.ptr(wfp), _lib.ptr(bfp), _lib.ptr(sfp),
+                                                 _lib.ptr(stats), 1e-6, M, T, _lib.ptr(buf), 768, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    one = buf[:M]
+    assert bool((buf[M:] == 7.0).all())
+    assert bool(torch.isfinite(one.float()).all())
+    y = torch.nn.functional.layer_norm(x.double(), (768,), gamma.double(), beta.double(), 1e-6) @ W.double().t() + b.double()
+    q, k, v = (y[:, i * 768:(i + 1) * 768].view(n_seq, T, 12, 64).transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(M, 768)
+    assert _rel(one.float(), ref) < 8e-3
+    assert _rel(two.float(), ref) < 8e-3
+    if T in (16, 32, 64):
+        assert torch.equal(one, two)          # same arithmetic in the same order: same bits
+    else:
+        assert _rel(one.float(), two.float()) < 4e-3
+
+
+def test_fused_temporal_qkv_attention_rejects_long_sequences(dev):
+    L = _lib.lib()
+    z = torch.zeros(65 * 2, 768, device=dev, dtype=torch.bfloat16)
+    f = torch.zeros(2304, device=dev)
+    rc = L.dvst_gemm_ln_temporal_attention(_lib.ptr(z), 768, _lib.ptr(torch.zeros(2304, 768, device=dev).bfloat16()),
+                                           _lib.ptr(f), _lib.ptr(f), _lib.ptr(torch.zeros(130, 12, device=dev)), 1e-6,
+                                           130, 65, _lib.ptr(z.clone()), 768, _lib.cur_stream())
+    assert rc != 0 and b"not covered" in L.dvst_last_error()

@@ -160,6 +160,35 @@ def test_deferred_layernorm_matches_standalone_layernorm(dev):
         assert _rel(f1, f0) < 1.5e-2 and _rel(a1, a0) < 1.5e-2   # two bf16 paths, each ~6e-3 from fp32
 
 
+@pytest.mark.parametrize("T,crop", [(16, 224), (8, 96), (3, 224), (30, 96), (32, 96), (5, 96)])
+def test_fused_temporal_half_matches_two_kernel_form(dev, T, crop):
+    """The temporal half of a divided block runs as ONE kernel by default (qkv GEMM whose epilogue does the temporal
+    attention out of shared memory, csrc/gemm_tattn_sm100.cu).  Against the two-kernel form: 12 launches fewer per depth-12
+    forward... here one per block; identical features for T in {16, 32} (same arithmetic, same order), bf16-rounding-level
+    agreement otherwise (sequences share 16-row MMA tiles, so the tensor core sums the same products in another order)."""
+    from dvst_b200 import _lib
+    L = _lib.lib()
+    m = build(dev, 5, 3, "divided_space_time", "bf16")
+    x = synth_clips(43, 3, T, crop, crop).to(dev)
+    try:
+        with torch.no_grad():
+            L.dvst_set_temporal_fusion(0)
+            n0 = _lib.launch_count()
+            f0, a0 = m(x), m.forward_features(x, get_all=True)
+            n_two = _lib.launch_count() - n0
+            L.dvst_set_temporal_fusion(1)
+            n0 = _lib.launch_count()
+            f1, a1 = m(x), m.forward_features(x, get_all=True)
+            n_one = _lib.launch_count() - n0
+    finally:
+        L.dvst_set_temporal_fusion(1)
+    assert n_two - n_one == 2 * 3                      # one launch fewer per block and forward
+    if T in (16, 32):
+        assert torch.equal(f0, f1) and torch.equal(a0, a1)
+    else:
+        assert _rel(f1, f0) < 6e-3 and _rel(a1, a0) < 6e-3
+
+
 @pytest.mark.parametrize("prec", ["bf16", "high"])
 def test_attention_map_vs_reference_golden(dev, prec):
     """forward_features(x, get_attn=True): last block's spatial attention map, against the reference's own output."""
