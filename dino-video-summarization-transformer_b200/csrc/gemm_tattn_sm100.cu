@@ -70,6 +70,19 @@ constexpr int NUM_OBOX = 2 * ATT_WARPS;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + ACC_STAGES * QKV_BYTES + NUM_OBOX * OBOX_BYTES + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
+__device__ __forceinline__ float4 ldg_f4_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_f4_keep(const float4* p) {
+  float4 r;
+  asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
 struct TAttnParams {
   int M;             // patch-token rows
   int T, R;          // frames per sequence, rows per CTA tile (whole sequences)
@@ -206,7 +219,9 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       float ln_rstd = 0.f, ln_nmr = 0.f;
       if (grow < p.M) {
         const float4* sp = reinterpret_cast<const float4*>(p.ln_stats) + grow * 3;
-        const float4 a0 = __ldg(sp), a1 = __ldg(sp + 1), a2 = __ldg(sp + 2);  // 6 x (sum, sumsq) per 128 columns
+        // 6 x (sum, sumsq) per 128 columns; streamed once per tile: kept out of the (28 KiB) L1 so that the bias / column-sum
+        // vectors of the 12 heads (18 KiB, re-read by every tile) stay resident
+        const float4 a0 = ldg_f4_stream(sp), a1 = ldg_f4_stream(sp + 1), a2 = ldg_f4_stream(sp + 2);
         const float mean = (((a0.x + a0.z) + (a1.x + a1.z)) + (a2.x + a2.z)) * (1.0f / 768.0f);
         const float var = (((a0.y + a0.w) + (a1.y + a1.w)) + (a2.y + a2.w)) * (1.0f / 768.0f) - mean * mean;
         ln_rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
@@ -240,8 +255,12 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t w[16];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + j4);
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + gcol) + j4);
+#ifdef DVST_TATTN_EXP_NO_LDG
+          const float4 b4 = make_float4(0.1f, 0.2f, 0.3f, 0.4f), s4 = make_float4(1.f, 2.f, 3.f, 4.f);
+#else
+          const float4 b4 = ldg_f4_keep(reinterpret_cast<const float4*>(p.bias + gcol) + j4);
+          const float4 s4 = ldg_f4_keep(reinterpret_cast<const float4*>(p.ln_colsum + gcol) + j4);
+#endif
           float fa, fb;
           unpk2(fma2(rstd2, f2[2 * j4], fma2(nmr2, pk2(s4.x, s4.y), pk2(b4.x, b4.y))), fa, fb);
           w[2 * j4] = pack2(fa, fb);
@@ -304,6 +323,9 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(sfull_bar + 8 * a, aph);
 #pragma unroll
       for (int qt = 0; qt < 2; ++qt) {
+#ifdef DVST_TATTN_EXP_NO_ATTENTION
+        continue;
+#endif
         if (n_valid[qt] == 0) continue;
         const int r0 = 32 * wq + 16 * qt;
         const int k0 = key0[qt];
