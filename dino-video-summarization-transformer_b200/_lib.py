@@ -119,7 +119,7 @@ def launch_count():
     return int(lib().dvst_launch_count())
 
 
-PROF_KINDS = ("gemm", "attention", "layernorm", "elementwise", "head_loss", "gemm_hbm")
+PROF_KINDS = ("gemm", "attention", "layernorm", "elementwise", "head_loss", "gemm_hbm", "gemm_tattn")
 
 
 def profile_enable(on):

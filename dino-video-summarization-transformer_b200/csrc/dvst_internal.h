@@ -24,8 +24,9 @@ template <class T> struct PerDevice {
 // Optional live per-kernel timing (CUDA events on the launching stream), used by bench.py for the roofline figures.
 // PROF_GEMM_HBM: short-K (K <= 1024) deferred-LayerNorm producer GEMMs - bounded by their residual / output streams (work is
 // counted in bytes), unlike every other GEMM launch (tensor bound, work in FLOPs).
+// PROF_GEMM_TATTN: the fused qkv-GEMM + temporal-attention kernel (gemm_tattn_sm100.cu), work in FLOPs (GEMM + attention).
 enum ProfKind { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_ELEMENTWISE = 3, PROF_HEAD_LOSS = 4,
-                PROF_GEMM_HBM = 5, PROF_NKINDS = 6 };
+                PROF_GEMM_HBM = 5, PROF_GEMM_TATTN = 6, PROF_NKINDS = 7 };
 struct ProfScope {
   int idx;
   cudaStream_t st;

@@ -57,7 +57,7 @@ constexpr int ACC_STRIDE = 256;                 // TMEM columns between the two 
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;       // drain warps
 constexpr int FIRST_EPI_WARP = 4;
-constexpr int ATT_WARPS = 4;
+constexpr int ATT_WARPS = 8;
 constexpr int FIRST_ATT_WARP = FIRST_EPI_WARP + EPI_WARPS;
 constexpr int NUM_THREADS = (FIRST_ATT_WARP + ATT_WARPS) * 32;
 constexpr int A_BYTES = BM * BK * 2;            // 16 KiB
@@ -66,7 +66,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int QKV_PITCH = 3 * 128;              // staging row: q | k | v, 128 bytes each
 constexpr int QKV_BYTES = BM * QKV_PITCH;       // 48 KiB
 constexpr int OBOX_BYTES = 16 * 128;            // one warp's output box
-constexpr int NUM_OBOX = 2 * ATT_WARPS;
+constexpr int NUM_OBOX = ATT_WARPS;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + ACC_STAGES * QKV_BYTES + NUM_OBOX * OBOX_BYTES + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -157,6 +157,12 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int tile_step = gridDim.x / 2;
   constexpr int NK = KD / BK;
 
+  // Register budget per role (640 threads -> 96 by default, i.e. a pool of 61 440 for the CTA): the producer / MMA /
+  // allocator warpgroup gives registers back (40), the two drain warpgroups (a 32-column accumulator slice in flight next
+  // to the one being folded and packed) take them (120), the attention warpgroups keep 96: 128 x 40 + 256 x 120 + 256 x 96
+  // = 60 416 <= 61 440 (a request beyond the pool blocks for ever).
+  if (warp < FIRST_EPI_WARP) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
   if (warp == 0) {
     int s = 0;
     uint32_t ph = 0;
@@ -203,7 +209,9 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= FIRST_EPI_WARP && warp < FIRST_ATT_WARP) {
+  }
+  } else if (warp < FIRST_ATT_WARP) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;" ::: "memory");
     // ---- drain: accumulators -> folded LayerNorm -> bf16 q | k | v of this head in shared memory ----
     const int e = warp - FIRST_EPI_WARP;
     const int q = warp & 3;   // TMEM lane quarter this warp may access
@@ -278,40 +286,35 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) mbar_arrive(sfull_bar + 8 * a);
       if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
     }
-  } else if (warp >= FIRST_ATT_WARP) {
-    // ---- temporal attention of query rows [32 w, 32 w + 32) of the CTA tile, one head per tile ----
+  } else {
+    // ---- temporal attention of query rows [16 w, 16 w + 16) of the CTA tile, one head per tile ----
     const int wq = warp - FIRST_ATT_WARP;
     const int g = lane >> 2, tig = lane & 3;
     const int mat = lane >> 3, r8 = lane & 7;
     const int T = p.T, R = p.R;
-    // geometry of the two 16-row query tiles (the same for every tile of the launch)
-    int key0[2], n_valid[2];
-    uint32_t vm0[2], vm1[2];  // bit (2 nt + j): key key0 + 8 nt + 2 tig + j belongs to the sequence of row r0 + g / + 8
+    // geometry of this warp's 16-row query tile (the same for every tile of the launch)
+    const int r0 = 16 * wq;
+    const int n_valid = R - r0 < 0 ? 0 : (R - r0 > 16 ? 16 : R - r0);
+    int k0 = 0;
+    uint32_t m0 = 0, m1 = 0;  // bit (2 nt + j): key k0 + 8 nt + 2 tig + j belongs to the sequence of row r0 + g / + 8
     constexpr uint32_t ALL_KEYS = MAXP == 4 ? 0xFFFFu : ((1u << (4 * MAXP)) - 1u);
+    if (n_valid > 0) {
+      k0 = (r0 / T) * T;
+      if (k0 > BM - 16 * MAXP) k0 = BM - 16 * MAXP;
+      const int ra = r0 + g < R ? r0 + g : r0, rb = r0 + g + 8 < R ? r0 + g + 8 : r0;
+      const int sa = ra / T, sb = rb / T;
 #pragma unroll
-    for (int qt = 0; qt < 2; ++qt) {
-      const int r0 = 32 * wq + 16 * qt;
-      n_valid[qt] = R - r0 < 0 ? 0 : (R - r0 > 16 ? 16 : R - r0);
-      key0[qt] = 0;
-      vm0[qt] = vm1[qt] = 0;
-      if (n_valid[qt] > 0) {
-        int k0 = (r0 / T) * T;
-        if (k0 > BM - 16 * MAXP) k0 = BM - 16 * MAXP;
-        key0[qt] = k0;
-        const int ra = r0 + g < R ? r0 + g : r0, rb = r0 + g + 8 < R ? r0 + g + 8 : r0;
-        const int sa = ra / T, sb = rb / T;
+      for (int nt = 0; nt < 2 * MAXP; ++nt) {
 #pragma unroll
-        for (int nt = 0; nt < 2 * MAXP; ++nt) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int k = k0 + nt * 8 + tig * 2 + j;
-            const int ks = k < R ? k / T : -1;
-            if (ks == sa) vm0[qt] |= 1u << (2 * nt + j);
-            if (ks == sb) vm1[qt] |= 1u << (2 * nt + j);
-          }
+        for (int j = 0; j < 2; ++j) {
+          const int k = k0 + nt * 8 + tig * 2 + j;
+          const int ks = k < R ? k / T : -1;
+          if (ks == sa) m0 |= 1u << (2 * nt + j);
+          if (ks == sb) m1 |= 1u << (2 * nt + j);
         }
       }
     }
+    const uint32_t obox = sO + wq * OBOX_BYTES;
     const float scale_log2 = 0.125f * 1.4426950408889634f;
     int a = 0;
     uint32_t aph = 0;
@@ -321,16 +324,8 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int tile_row0 = (m_blk * 2 + static_cast<int>(cta_rank)) * R;
       const uint32_t sT = sQKV + a * QKV_BYTES;
       mbar_wait(sfull_bar + 8 * a, aph);
-#pragma unroll
-      for (int qt = 0; qt < 2; ++qt) {
-#ifdef DVST_TATTN_EXP_NO_ATTENTION
-        continue;
-#endif
-        if (n_valid[qt] == 0) continue;
-        const int r0 = 32 * wq + 16 * qt;
-        const int k0 = key0[qt];
-        const uint32_t m0 = vm0[qt], m1 = vm1[qt];
-        const uint32_t obox = sO + (2 * wq + qt) * OBOX_BYTES;
+#ifndef DVST_TATTN_EXP_NO_ATTENTION
+      if (n_valid > 0) {
         uint32_t qa[4][4];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -406,11 +401,8 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-        // the TMA store of this box's previous tile must have finished reading it (at most the other box's store pending)
-        if (elect_one()) {
-          if (n_valid[1] > 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // only one box in use
-        }
+        // the TMA store of this box's previous tile must have finished reading it
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -423,7 +415,7 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(orow + ((dt ^ (lr & 7)) << 4)), "r"(hv) : "memory");
           }
         }
-        if (n_valid[qt] == 16) {
+        if (n_valid == 16) {
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
@@ -440,16 +432,16 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int idx = lane + 32 * i;
             const int lr = idx >> 3, ch = idx & 7;
             const long long gr = static_cast<long long>(tile_row0) + r0 + lr;
-            if (lr < n_valid[qt] && gr < p.M) {
+            if (lr < n_valid && gr < p.M) {
               uint4 val;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                            : "r"(obox + lr * 128 + ((ch ^ (lr & 7)) << 4)) : "memory");
               *reinterpret_cast<uint4*>(p.out + gr * p.ldo + head * 64 + ch * 8) = val;
             }
           }
-          if (elect_one()) asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // keeps one group per box and tile
         }
       }
+#endif
       __syncwarp();  // every lane has read its q / k / v fragments of this buffer
       if (lane == 0) mbar_arrive(sempty_bar + 8 * a);
       if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
@@ -518,7 +510,7 @@ static int launch_tattn_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ProfScope prof(PROF_GEMM, flops, stream);
+  ProfScope prof(PROF_GEMM_TATTN, flops, stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_ln_tattn_kernel<MAXP>, tmA, tmB, tmO, p);
   if (e != cudaSuccess) return set_error("gemm_ln_tattn launch: %s", cudaGetErrorString(e));
   count_launch();

@@ -67,7 +67,7 @@ void dvst_set_chunk_rows(long long rows);
 /* Live per-kernel timing for bench.py's roofline: while enabled, every launch is bracketed by CUDA events on its own
  * stream.  dvst_profile_collect waits for the recorded events, sums elapsed ms / work (FLOPs for kind 0 GEMM and
  * 1 attention, bytes for 2 layernorm, 3 elementwise, 4 head-loss, 5 the HBM-bound short-K deferred-LayerNorm producer
- * GEMMs) / launch counts per kind, and clears the log. */
+ * GEMMs, FLOPs for 6 the fused qkv-GEMM + temporal-attention kernel) / launch counts per kind, and clears the log. */
 void dvst_profile_enable(int on);
 int dvst_profile_collect(double* ms, double* work, long long* count, int nkinds);
 
