@@ -59,6 +59,7 @@ const char* dvst_last_error(void) { return g_err; }
 long long dvst_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int dvst_abi_version(void) { return DVST_ABI_VERSION; }
 void dvst_set_gemm_cta_group(int cg) { set_gemm_cta_group(cg); }
+void dvst_set_producer_ring(int r) { set_producer_ring(r); }
 void dvst_set_attention_impl(int impl) { set_attention_impl(impl); }
 
 void dvst_profile_enable(int on) {

@@ -62,6 +62,7 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 void set_gemm_cta_group(int cg);  // 1 or 2 (default 2); tuning / test hook
+void set_producer_ring(int r);    // 5 (default) or 3 residual boxes per epilogue warp of the short-K producers; tuning hook
 
 // Temporal half of a divided block in one kernel (gemm_tattn_sm100.cu): deferred-LayerNorm qkv GEMM whose epilogue runs the
 // temporal attention out of shared memory; the packed qkv tensor is never written.  w / bias / colsum are HEAD-PERMUTED

@@ -53,13 +53,20 @@ constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 // kCG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256x256 tile; each CTA stages its 128 A rows and
 //          HALF of the W tile (32 KiB / stage, 6 stages) - the tensor core reads the other half from the peer's shared
 //          memory, which halves the L2->SM operand traffic per FLOP (the 1-CTA kernel saturates L2 bandwidth).
-template <int kCG> struct Cfg {
+// kRing: residual boxes per epilogue warp of the deferred-LayerNorm producers (kOut = 3).  3 = the default (loads two chunks
+// ahead); 5 = the short-K producers (K = 768: patch-embed, temporal proj*fc, proj), which are bound by their fp32 residual
+// stream, not by the tensor core: one operand stage is traded for two more 4 KiB boxes per warp so that the residual loads
+// run four chunks (64 KiB per CTA) ahead (ncu: 40 % of the epilogue warps' time was the wait for a residual box).
+template <int kCG, int kRing = 3> struct Cfg {
   static constexpr int B_ROWS = BN / kCG;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = kCG == 1 ? 3 : 5;
-  static constexpr int EPI_BYTES = EPI_WARPS * STG_BYTES;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+  static constexpr int STAGES = kCG == 1 ? 3 : (kRing > 3 ? 4 : 5);
+  static constexpr int PRODUCER_WARP_BYTES = kRing * STG_BUF_BYTES + STG_BUF_BYTES;  // ring + two 2 KiB bf16 boxes
+  static constexpr int EPI_BYTES = kRing > 3 ? 4 * PRODUCER_WARP_BYTES : EPI_WARPS * STG_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct GemmParams {
@@ -159,14 +166,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // so the epilogue (issue-bound next to the 256x256x768 MMA of fc1) carries no predicated code of the other modes.
 // kOut = 3: fp32 in-place residual (TMA load + add + TMA store) + bf16 copy + row statistics (deferred LayerNorm producer).
 // kLN = 1: deferred LayerNorm consumer (bf16 output only).
-template <int kCG, int kOut, int kAct, int kLN>
+template <int kCG, int kOut, int kAct, int kLN, int kRing = 3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmXb,
                     const GemmParams p) {
   constexpr int EW = kOut == 3 ? 4 : EPI_WARPS;  // epilogue warps that take part
   constexpr bool kProducer = kOut == 3;
-  using C = Cfg<kCG>;
+  using C = Cfg<kCG, kRing>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -182,7 +189,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tfull_bar = bars + 16 * STAGES;        // [ACC_STAGES]
   const uint32_t tempty_bar = tfull_bar + 8 * ACC_STAGES;  // (2-CTA: only the leader's copy is used)
   const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
-  const uint32_t res_bar = tmem_slot + 8;                // producers: [EW warps][3 ring slots]
+  const uint32_t res_bar = tmem_slot + 8;                // producers: [EW warps][kRing ring slots]
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5;
@@ -206,7 +213,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(tempty_bar + 8 * a, EW * kCG);
     }
     if constexpr (kProducer) {
-      for (int i = 0; i < 3 * EW; ++i) mbar_init(res_bar + 8 * i, 1);
+      for (int i = 0; i < kRing * EW; ++i) mbar_init(res_bar + 8 * i, 1);
     }
     fence_mbar_init();
   }
@@ -339,9 +346,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr int NCH = 8;
       constexpr int col_base = 0;
       if (e < EW) {
-        const uint32_t ring = stg_all + e * (2 * STG_BYTES);
-        const uint32_t bst = ring + 3 * STG_BUF_BYTES;
-        const uint32_t rbar = res_bar + e * 24;
+        const uint32_t ring = stg_all + e * C::PRODUCER_WARP_BYTES;
+        const uint32_t bst = ring + kRing * STG_BUF_BYTES;
+        const uint32_t rbar = res_bar + e * (8 * kRing);
         const uint32_t brow_off = lane * 64;
         const int bsw = (lane >> 1) & 3;
         int l_tile = tile0, l_c = 0;
@@ -349,7 +356,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         auto issue_load = [&]() {  // lane 0 only
           if (l_tile < num_tiles) {
             const int lm = l_tile / p.num_n_blocks, ln = l_tile % p.num_n_blocks;
-            const uint32_t sl = l_g % 3;
+            const uint32_t sl = l_g % kRing;
             mbar_arrive_expect_tx(rbar + 8 * sl, STG_BUF_BYTES);
             tma_load_2d(ring + sl * STG_BUF_BYTES, &tmO, rbar + 8 * sl, ln * BN + col_base + l_c * 32,
                         (lm * kCG + static_cast<int>(cta_rank)) * BM + q * 32);
@@ -357,7 +364,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++l_c == NCH) { l_c = 0; l_tile += tile_step; }
           }
         };
-        if (elect_one()) { issue_load(); issue_load(); }
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < kRing - 1; ++i) issue_load();
+        }
         uint32_t g = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
           const int m_blk = tile / p.num_n_blocks;
@@ -376,8 +386,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
           for (int c = 0; c < NCH; ++c, ++g) {
             const int gcol0 = n_blk * BN + col_base + c * 32;
-            const uint32_t sl = g % 3;
-            mbar_wait(rbar + 8 * sl, (g / 3) & 1);
+            const uint32_t sl = g % kRing;
+            mbar_wait(rbar + 8 * sl, (g / kRing) & 1);
             tmem_ld_wait();
             float w[32];
 #pragma unroll
@@ -430,7 +440,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                              "r"(grow) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               // the stores of the previous chunk have finished reading their boxes: its ring slot takes the load that
-              // runs two chunks ahead, its bf16 box is the next chunk's
+              // runs kRing - 1 chunks ahead, its bf16 box is the next chunk's
               asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
               issue_load();
             }
@@ -653,16 +663,18 @@ int num_sms() {
   return n;
 }
 
+static int g_producer_ring = 5;
+void set_producer_ring(int r) { g_producer_ring = r > 3 ? 5 : 3; }
 static int g_gemm_cta_group = 2;
 void set_gemm_cta_group(int cg) { g_gemm_cta_group = cg == 1 ? 1 : 2; }
 
-template <int kCG, int kOut, int kAct, int kLN>
+template <int kCG, int kOut, int kAct, int kLN, int kRing = 3>
 static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
-  using C = Cfg<kCG>;
+  using C = Cfg<kCG, kRing>;
   static PerDevice<bool> attr_cache;
   bool& attr_set = attr_cache.get();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kCG, kOut, kAct, kLN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<kCG, kOut, kAct, kLN, kRing>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -706,7 +718,7 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   const double hbm_bytes = static_cast<double>(g.M) * (2.0 * g.K + 10.0 * g.N) + 2.0 * g.N * g.K;  // A, x in / out, xb, W
   ProfScope prof(hbm_bound ? PROF_GEMM_HBM : PROF_GEMM,
                  hbm_bound ? hbm_bytes : 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG, kOut, kAct, kLN>, tmA, tmB, tmO, tmXb, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<kCG, kOut, kAct, kLN, kRing>, tmA, tmB, tmO, tmXb, p);
   if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -745,7 +757,11 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     if (g.act == 0) return cg2 ? launch_gemm_impl<2, 0, 0, 1>(g, stream) : launch_gemm_impl<1, 0, 0, 1>(g, stream);
     return cg2 ? launch_gemm_impl<2, 0, 1, 1>(g, stream) : launch_gemm_impl<1, 0, 1, 1>(g, stream);
   }
-  if (g.out_kind == 3) return cg2 ? launch_gemm_impl<2, 3, 0, 0>(g, stream) : launch_gemm_impl<1, 3, 0, 0>(g, stream);
+  if (g.out_kind == 3) {
+    if (!cg2) return launch_gemm_impl<1, 3, 0, 0>(g, stream);
+    // short K: bound by the residual stream - deeper residual prefetch, one operand stage fewer
+    return g.K <= 1024 && g_producer_ring > 3 ? launch_gemm_impl<2, 3, 0, 0, 5>(g, stream) : launch_gemm_impl<2, 3, 0, 0>(g, stream);
+  }
 #define DVST_GEMM_CASE(OUT, ACT)                                                                   \
   if (g.out_kind == OUT && g.act == ACT)                                                           \
     return cg2 ? launch_gemm_impl<2, OUT, ACT, 0>(g, stream) : launch_gemm_impl<1, OUT, ACT, 0>(g, stream);

@@ -46,6 +46,10 @@ int dvst_abi_version(void);
  * single-CTA 128x256 kernel. */
 void dvst_set_gemm_cta_group(int cg);
 
+/* Tuning / test hook: residual boxes per epilogue warp of the K <= 1024 deferred-LayerNorm producer GEMMs: 5 (default,
+ * residual loads four chunks ahead, four operand stages) or 3 (two ahead, five operand stages).  Same results. */
+void dvst_set_producer_ring(int boxes);
+
 /* Tuning / test hook: 1 (default) runs spatial / space-only attention (modes 1 and 3, up to 256 tokens, bf16) on the
  * tcgen05 + TMEM kernel (one-pass softmax where scratch is available); 2 the same kernel with the two-pass softmax;
  * 0 forces the mma.sync kernels for every mode. */
