@@ -94,8 +94,8 @@ int dvst_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, c
 
 int dvst_gemm_ln_temporal_attention(const void* xb, long long ldxb, const void* w_perm, const float* bias_perm,
                                     const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T,
-                                    void* out, long long ldo, void* stream) {
-  const int rc = launch_gemm_ln_tattn(xb, ldxb, w_perm, bias_perm, colsum_perm, ln_stats, ln_eps, M, T, out, ldo,
+                                    long long clip_rows, void* out, long long ldo, void* stream) {
+  const int rc = launch_gemm_ln_tattn(xb, ldxb, w_perm, bias_perm, colsum_perm, ln_stats, ln_eps, M, T, clip_rows, out, ldo,
                                       static_cast<cudaStream_t>(stream));
   if (rc < 0) return set_error("dvst_gemm_ln_temporal_attention: T = %d is not covered (1 <= T <= 64)", T);
   return rc;

@@ -66,11 +66,12 @@ void set_producer_ring(int r);    // 5 (default) or 3 residual boxes per epilogu
 
 // Temporal half of a divided block in one kernel (gemm_tattn_sm100.cu): deferred-LayerNorm qkv GEMM whose epilogue runs the
 // temporal attention out of shared memory; the packed qkv tensor is never written.  w / bias / colsum are HEAD-PERMUTED
-// (row 192 h + 64 part + d = original row 768 part + 64 h + d).  Returns 0 when it ran, -1 when T is not covered (T > 64:
+// (row 192 h + 64 part + d = original row 768 part + 64 h + d).  clip_rows (0 = M): the rows are tiled clip by clip (every clip
+// the same way, tiles never straddle a clip), so a sequence's place inside its MMA tile does not depend on the batch.  Returns 0 when it ran, -1 when T is not covered (T > 64:
 // callers run the qkv GEMM + temporal attention kernels), DVST_ERR (1) on error.
 int launch_gemm_ln_tattn(const void* xb, long long ldxb, const void* w_perm, const float* bias_perm,
-                         const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T, void* out,
-                         long long ldo, cudaStream_t stream);
+                         const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T,
+                         long long clip_rows, void* out, long long ldo, cudaStream_t stream);
 void set_temporal_fusion(int on);  // 1 (default) use the fused kernel where the permuted tensors are registered
 int temporal_fusion();
 

@@ -86,7 +86,9 @@ __device__ __forceinline__ float4 ldg_f4_keep(const float4* p) {
 struct TAttnParams {
   int M;             // patch-token rows
   int T, R;          // frames per sequence, rows per CTA tile (whole sequences)
-  int num_m_blocks;  // CTA-pair tiles of 2 R rows
+  int num_m_blocks;  // CTA-pair tiles (two CTA tiles each)
+  int clip_rows;     // rows per clip (tiles never straddle a clip: every clip is tiled the same way), a multiple of T
+  int tiles_per_clip;  // ceil(clip_rows / R) CTA tiles
   const float* bias;       // fp32 [2304], head-permuted: b + W beta
   const float* ln_colsum;  // fp32 [2304], head-permuted row sums of the folded weight
   const float* ln_stats;   // fp32 [M, 6, 2]
@@ -94,6 +96,14 @@ struct TAttnParams {
   __nv_bfloat16* out;      // [M, ldo] (plain stores of partially valid boxes)
   long long ldo;
 };
+
+// First row and number of rows of CTA tile `ct`: clip ct / tiles_per_clip, R rows per tile, the clip's last tile shorter.
+__device__ __forceinline__ void cta_tile_rows(const TAttnParams& p, int ct, int& row0, int& rows) {
+  const int clip = ct / p.tiles_per_clip, j = ct - clip * p.tiles_per_clip;
+  row0 = clip * p.clip_rows + j * p.R;
+  rows = p.clip_rows - j * p.R;
+  if (rows > p.R) rows = p.R;
+}
 
 // MAXP: 16-key pairs of n-tiles in the key block (key block = 16 MAXP keys).
 template <int MAXP>
@@ -170,7 +180,8 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / NUM_HEADS;
       const int head = tile - m_blk * NUM_HEADS;
-      const int row_a = (m_blk * 2 + static_cast<int>(cta_rank)) * p.R;
+      int row_a, rows_a;
+      cta_tile_rows(p, m_blk * 2 + static_cast<int>(cta_rank), row_a, rows_a);
       const int row_b = head * HN + static_cast<int>(cta_rank) * (HN / 2);
       for (int it = 0; it < NK; ++it) {
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -223,7 +234,9 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / NUM_HEADS;
       const int head = tile - m_blk * NUM_HEADS;
-      const long long grow = static_cast<long long>(m_blk * 2 + static_cast<int>(cta_rank)) * p.R + lrow;
+      int tile_row0, tile_rows;
+      cta_tile_rows(p, m_blk * 2 + static_cast<int>(cta_rank), tile_row0, tile_rows);
+      const long long grow = static_cast<long long>(tile_row0) + lrow;
       float ln_rstd = 0.f, ln_nmr = 0.f;
       if (grow < p.M) {
         const float4* sp = reinterpret_cast<const float4*>(p.ln_stats) + grow * 3;
@@ -321,11 +334,13 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / NUM_HEADS;
       const int head = tile - m_blk * NUM_HEADS;
-      const int tile_row0 = (m_blk * 2 + static_cast<int>(cta_rank)) * R;
+      int tile_row0, tile_rows;
+      cta_tile_rows(p, m_blk * 2 + static_cast<int>(cta_rank), tile_row0, tile_rows);
+      const int nv = tile_rows - r0 < n_valid ? tile_rows - r0 : n_valid;  // valid query rows of this warp in this tile
       const uint32_t sT = sQKV + a * QKV_BYTES;
       mbar_wait(sfull_bar + 8 * a, aph);
 #ifndef DVST_TATTN_EXP_NO_ATTENTION
-      if (n_valid > 0) {
+      if (nv > 0) {
         uint32_t qa[4][4];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -415,7 +430,7 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(orow + ((dt ^ (lr & 7)) << 4)), "r"(hv) : "memory");
           }
         }
-        if (n_valid == 16) {
+        if (nv == 16) {
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
@@ -432,7 +447,7 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int idx = lane + 32 * i;
             const int lr = idx >> 3, ch = idx & 7;
             const long long gr = static_cast<long long>(tile_row0) + r0 + lr;
-            if (lr < n_valid && gr < p.M) {
+            if (lr < nv && gr < p.M) {
               uint4 val;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                            : "r"(obox + lr * 128 + ((ch ^ (lr & 7)) << 4)) : "memory");
@@ -519,12 +534,15 @@ static int launch_tattn_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, con
 
 // 0 = ran, -1 = shape not covered (the caller runs the qkv GEMM and the temporal attention kernel), DVST_ERR = error
 int launch_gemm_ln_tattn(const void* xb, long long ldxb, const void* w_perm, const float* bias_perm,
-                         const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T, void* out,
-                         long long ldo, cudaStream_t stream) {
+                         const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T,
+                         long long clip_rows, void* out, long long ldo, cudaStream_t stream) {
   int R = 0, maxp = 0;
   if (!tattn_geometry(T, &R, &maxp)) return -1;
   if (M <= 0) return 0;
   if (M % T != 0) return set_error("gemm_ln_tattn: %lld rows are not whole sequences of %d", M, T);
+  if (clip_rows <= 0) clip_rows = M;
+  if (clip_rows % T != 0 || M % clip_rows != 0)
+    return set_error("gemm_ln_tattn: clip_rows = %lld must be a multiple of T = %d and divide M = %lld", clip_rows, T, M);
   if (M > 2000000000LL) return set_error("gemm_ln_tattn: too many rows");
   if ((reinterpret_cast<uintptr_t>(xb) & 15) || (reinterpret_cast<uintptr_t>(w_perm) & 15) || (ldxb % 8) ||
       (reinterpret_cast<uintptr_t>(out) & 15) || (ldo % 8) || (reinterpret_cast<uintptr_t>(ln_stats) & 15) ||
@@ -536,7 +554,10 @@ int launch_gemm_ln_tattn(const void* xb, long long ldxb, const void* w_perm, con
   if (int rc = make_tmap_2d(&tmO, out, 2, static_cast<uint64_t>(M), KD, ldo, 16, 64, false)) return rc;
   TAttnParams p;
   p.M = static_cast<int>(M); p.T = T; p.R = R;
-  p.num_m_blocks = static_cast<int>((M + 2LL * R - 1) / (2LL * R));
+  p.clip_rows = static_cast<int>(clip_rows);
+  p.tiles_per_clip = static_cast<int>((clip_rows + R - 1) / R);
+  const long long cta_tiles = (M / clip_rows) * p.tiles_per_clip;
+  p.num_m_blocks = static_cast<int>((cta_tiles + 1) / 2);
   p.bias = bias_perm; p.ln_colsum = colsum_perm; p.ln_stats = ln_stats; p.ln_eps = ln_eps;
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
   // executed work: the qkv GEMM as launched plus 4 T^2 64 FLOPs per (sequence, head)

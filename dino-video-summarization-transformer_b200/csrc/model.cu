@@ -356,15 +356,17 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
     const BlockW& b = m->blocks[i];
     if (att == DVST_ATTN_DIVIDED) {
       // temporal attention over the T tokens of every (b, n); CLS rows excluded (:127-135)
-      // bf16 + deferred LayerNorm: qkv GEMM and temporal attention are ONE kernel, the qkv tensor stays in shared memory
-      // (gemm_tattn_sm100.cu).  The choice depends on the model and the clip shape only, never on the batch, and is limited
-      // to T in {1, 2, 4, 8, 16, 32, 64} with every clip starting on a 16-row boundary: each sequence then sits at the same
-      // place of its 16-row MMA tile whatever the batch composition, so features stay bit-identical between batched and
-      // one-at-a-time scoring (and equal to the two-kernel form).  Other T (the 4_3_30 windows T = 3, 30) keep two kernels.
+      // bf16 + deferred LayerNorm, T <= 64: qkv GEMM and temporal attention are ONE kernel, the qkv tensor stays in shared
+      // memory (gemm_tattn_sm100.cu).  The choice depends on the model and the clip shape only, never on the batch.
+      // T in {1, 2, 4, 8, 16, 32, 64} with clips that start on a 16-row boundary: rows tiled as one matrix - same bits as the
+      // two-kernel form.  Any other T (the 4_3_30 windows T = 3, 30): rows tiled clip by clip, so every sequence sits at a
+      // place of its MMA tile that depends on its patch index only and features stay bit-identical between batched and
+      // one-at-a-time scoring (they differ from the two-kernel form by the summation order inside the tensor core).
       int fused = -1;
-      const bool t_pow2 = T <= 64 && (T & (T - 1)) == 0;
-      if (fl && m->fused_tattn && temporal_fusion() && t_pow2 && (T >= 16 || (N * T) % 16 == 0)) {
-        fused = launch_gemm_ln_tattn(xb, D, b.tqkv_wfp, b.tqkv_bfp, b.tqkv_sfp, w.stats, LN_EPS, Mt, T, w.a, lda, st);
+      if (fl && m->fused_tattn && temporal_fusion() && T <= 64) {
+        const bool t_pow2 = (T & (T - 1)) == 0;
+        const long long clip_rows = t_pow2 && (T >= 16 || (N * T) % 16 == 0) ? 0 : N * T;
+        fused = launch_gemm_ln_tattn(xb, D, b.tqkv_wfp, b.tqkv_bfp, b.tqkv_sfp, w.stats, LN_EPS, Mt, T, clip_rows, w.a, lda, st);
         if (fused > 0) return fused;
       }
       if (fused != 0) {

@@ -192,10 +192,12 @@ int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw
  * shared memory and runs the temporal attention from there - the packed qkv tensor is never written.
  *   xb, ln_stats : as for the consumer form; M rows = whole sequences of T consecutive rows ((b, n, t) order), 1 <= T <= 64
  *   w_perm bf16 [2304, 768], bias_perm / colsum_perm fp32 [2304]: head-permuted (row 192 h + 64 part + d)
+ *   clip_rows: 0, or the rows per clip (N T; a multiple of T that divides M): rows are then tiled clip by clip, so that the
+ *       place of a sequence inside its MMA tile - and with it the rounding of its output - does not depend on the batch
  *   out bf16 [M, ldo]: attention output, head h in columns [64 h, 64 h + 64) - the A operand of the proj GEMM. */
 int dvst_gemm_ln_temporal_attention(const void* xb, long long ldxb, const void* w_perm, const float* bias_perm,
                                     const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T,
-                                    void* out, long long ldo, void* stream);
+                                    long long clip_rows, void* out, long long ldo, void* stream);
 /* nn.LayerNorm(768, eps) over M rows of fp32 (models/timesformer.py:99,105,112,245).  out_kind as above. */
 int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,
                       int out_kind, long long lo_off, long long M, float eps, void* stream);

@@ -546,9 +546,11 @@ def test_attention_high_precision_tcgen05(dev, mode, B, T, N, impl):
 
 
 # ---- temporal half of a divided block in one kernel: deferred-LayerNorm qkv GEMM + temporal attention out of shared memory
-@pytest.mark.parametrize("T,n_seq", [(16, 313), (16, 8), (32, 77), (64, 9), (8, 401), (4, 1000), (1, 300), (30, 131),
-                                     (3, 1571), (5, 52), (17, 40), (48, 7), (2, 64)])
-def test_fused_temporal_qkv_attention(dev, T, n_seq):
+@pytest.mark.parametrize("T,n_seq,clip_seqs", [(16, 313, 0), (16, 8, 0), (32, 77, 0), (64, 9, 0), (8, 401, 0), (4, 1000, 0),
+                                               (1, 300, 0), (30, 131, 0), (3, 1571, 0), (5, 52, 0), (17, 40, 0), (48, 7, 0),
+                                               (2, 64, 0), (30, 196 * 3, 196), (3, 196 * 7, 196), (16, 196 * 3, 196),
+                                               (5, 36 * 4, 36), (8, 49 * 5, 49)])
+def test_fused_temporal_qkv_attention(dev, T, n_seq, clip_seqs):
     """dvst_gemm_ln_temporal_attention vs the two-kernel form (dvst_gemm_bf16_ln consumer -> dvst_attention mode 0) and vs
     an fp64 torch statement of temporal_norm1 -> qkv -> softmax(q k^T / 8) v (models/timesformer.py:127-131, :68-81).
     Tile tails (M not a multiple of the 2 x R tile), sequences that straddle 16-row query tiles (T = 30, 3, 5, 17) and
@@ -556,6 +558,7 @@ def test_fused_temporal_qkv_attention(dev, T, n_seq):
     torch.manual_seed(T * 1000 + n_seq)
     L = _lib.lib()
     M = T * n_seq
+    clip_rows = clip_seqs * T          # 0: one matrix; else rows are tiled clip by clip (clip_seqs sequences per clip)
     x = torch.randn(M, 768, device=dev) * 1.7 + 0.2
     x[:, 5] += 9.0
     gamma = torch.randn(768, device=dev) * 0.1 + 1.0
@@ -580,7 +583,8 @@ def test_fused_temporal_qkv_attention(dev, T, n_seq):
     guard = 64
     buf = torch.full((M + guard, 768), 7.0, device=dev, dtype=torch.bfloat16)   # rows past M must stay untouched
     _lib.check(L.dvst_gemm_ln_temporal_attention(_lib.ptr(xb), 768, _lib.ptr(wfp), _lib.ptr(bfp), _lib.ptr(sfp),
-                                                 _lib.ptr(stats), 1e-6, M, T, _lib.ptr(buf), 768, _lib.cur_stream()))
+                                                 _lib.ptr(stats), 1e-6, M, T, clip_rows, _lib.ptr(buf), 768,
+                                                 _lib.cur_stream()))
     torch.cuda.synchronize()
     one = buf[:M]
     assert bool((buf[M:] == 7.0).all())
@@ -594,6 +598,17 @@ def test_fused_temporal_qkv_attention(dev, T, n_seq):
         assert torch.equal(one, two)          # same arithmetic in the same order: same bits
     else:
         assert _rel(one.float(), two.float()) < 4e-3
+    if clip_rows:
+        # clip-by-clip tiling: the output of a clip does not depend on where it sits in the batch
+        n_clips = M // clip_rows
+        c = n_clips - 1
+        sl = slice(c * clip_rows, (c + 1) * clip_rows)
+        xb1, st1 = xb[sl].contiguous(), stats[sl].contiguous()
+        alone = torch.empty(clip_rows, 768, device=dev, dtype=torch.bfloat16)
+        _lib.check(L.dvst_gemm_ln_temporal_attention(_lib.ptr(xb1), 768, _lib.ptr(wfp), _lib.ptr(bfp), _lib.ptr(sfp),
+                                                     _lib.ptr(st1), 1e-6, clip_rows, T, clip_rows, _lib.ptr(alone), 768,
+                                                     _lib.cur_stream()))
+        assert torch.equal(alone, one[sl])
 
 
 def test_fused_temporal_qkv_attention_rejects_long_sequences(dev):
@@ -602,5 +617,5 @@ def test_fused_temporal_qkv_attention_rejects_long_sequences(dev):
     f = torch.zeros(2304, device=dev)
     rc = L.dvst_gemm_ln_temporal_attention(_lib.ptr(z), 768, _lib.ptr(torch.zeros(2304, 768, device=dev).bfloat16()),
                                            _lib.ptr(f), _lib.ptr(f), _lib.ptr(torch.zeros(130, 12, device=dev)), 1e-6,
-                                           130, 65, _lib.ptr(z.clone()), 768, _lib.cur_stream())
+                                           130, 65, 0, _lib.ptr(z.clone()), 768, _lib.cur_stream())
     assert rc != 0 and b"not covered" in L.dvst_last_error()

@@ -160,14 +160,14 @@ def test_deferred_layernorm_matches_standalone_layernorm(dev):
         assert _rel(f1, f0) < 1.5e-2 and _rel(a1, a0) < 1.5e-2   # two bf16 paths, each ~6e-3 from fp32
 
 
-@pytest.mark.parametrize("T,crop,fused", [(16, 224, True), (8, 96, True), (32, 96, True), (4, 96, True), (3, 224, False),
-                                          (30, 96, False), (8, 112, False)])
-def test_fused_temporal_half_matches_two_kernel_form(dev, T, crop, fused):
-    """The temporal half of a divided block (temporal_norm1 -> qkv -> attention) runs as ONE kernel for power-of-two T
-    (qkv GEMM whose epilogue does the temporal attention out of shared memory, csrc/gemm_tattn_sm100.cu): one launch fewer
-    per block, and the SAME BITS as the two-kernel form (same arithmetic in the same order).  Other T (the 4_3_30 windows
-    T = 3 / 30) and clips that do not start on a 16-row boundary (8 x 7 x 7 tokens) keep the two-kernel form, so that
-    features never depend on the batch composition."""
+@pytest.mark.parametrize("T,crop,same_bits", [(16, 224, True), (8, 96, True), (32, 96, True), (4, 96, True),
+                                              (3, 224, False), (30, 96, False), (8, 112, False), (5, 96, False)])
+def test_fused_temporal_half_matches_two_kernel_form(dev, T, crop, same_bits):
+    """The temporal half of a divided block (temporal_norm1 -> qkv -> attention) runs as ONE kernel for T <= 64 (qkv GEMM
+    whose epilogue does the temporal attention out of shared memory, csrc/gemm_tattn_sm100.cu): one launch fewer per block.
+    Power-of-two T on 16-row-aligned clips: the SAME BITS as the two-kernel form (same arithmetic in the same order).
+    Other shapes (the 4_3_30 windows T = 3 / 30, 8 x 7 x 7 tokens): rows are tiled clip by clip, the result agrees to bf16
+    rounding.  In every case the features do not depend on the batch composition."""
     from dvst_b200 import _lib
     L = _lib.lib()
     m = build(dev, 5, 3, "divided_space_time", "bf16")
@@ -183,11 +183,15 @@ def test_fused_temporal_half_matches_two_kernel_form(dev, T, crop, fused):
             f1, a1 = m(x), m.forward_features(x, get_all=True)
             n_one = _lib.launch_count() - n0
             single = torch.cat([m(x[i:i + 1]) for i in range(3)])
+            rev = m(x.flip(0)).flip(0)
     finally:
         L.dvst_set_temporal_fusion(1)
-    assert n_two - n_one == (2 * 3 if fused else 0)    # one launch fewer per block and forward
-    assert torch.equal(f0, f1) and torch.equal(a0, a1)
-    assert torch.equal(single, f1)                     # batch-composition independence
+    assert n_two - n_one == 2 * 3                      # one launch fewer per block and forward
+    if same_bits:
+        assert torch.equal(f0, f1) and torch.equal(a0, a1)
+    else:
+        assert _rel(f1, f0) < 6e-3 and _rel(a1, a0) < 6e-3
+    assert torch.equal(single, f1) and torch.equal(rev, f1)   # batch-composition independence
 
 
 @pytest.mark.parametrize("prec", ["bf16", "high"])

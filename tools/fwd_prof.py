@@ -13,7 +13,9 @@ reps = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 dev = torch.device("cuda:0")
 if len(sys.argv) > 5:
     _lib.lib().dvst_set_chunk_rows(int(sys.argv[5]))
-m = VisionTransformer(img_size=224, num_classes=0, depth=depth, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_frames=8)
+prec = os.environ.get("DVST_PRECISION", "bf16")   # "high" = 2-term bf16 split
+m = VisionTransformer(img_size=224, num_classes=0, depth=depth, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_frames=8,
+                      precision=prec)
 m.load_state_dict(synth_backbone_state_dict(0, depth=depth, num_frames=8), strict=True)
 m = m.eval().to(dev)
 x = torch.randn(B, 3, T, 224, 224, device=dev)

@@ -53,7 +53,7 @@ def run(T, n_seq):
 
     def fused():
         _lib.check(L.dvst_gemm_ln_temporal_attention(_lib.ptr(xb), 768, _lib.ptr(wfp), _lib.ptr(bp), _lib.ptr(sfp),
-                                                     _lib.ptr(stats), 1e-6, M, T, _lib.ptr(o1), 768, st))
+                                                     _lib.ptr(stats), 1e-6, M, T, 0, _lib.ptr(o1), 768, st))
 
     tg, ta, tf = timeit(gemm), timeit(att), timeit(fused)
     gemm(); att(); fused()
