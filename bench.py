@@ -638,10 +638,11 @@ def main_ours(args):
         achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         h_flops = h_n * 2.0 * (B_PER_GPU * 196 * T) * 768 * 768
         all_tf = (g_flops + h_flops + t_flops) / ((g_ms + h_ms + t_ms) / 1e3) / 1e12 if g_ms + h_ms + t_ms > 0 else 0.0
-        traffic = traffic_hbm = None
+        traffic = traffic_hbm = traffic_fused = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
             traffic, traffic_hbm = tj["dram_bytes_per_launch"], tj.get("dram_bytes_per_launch_hbm_gemm")
+            traffic_fused = tj.get("dram_bytes_per_launch_fused_temporal")
         except Exception:
             pass
         step_s = ms_max / args.steps / 1e3
@@ -674,7 +675,7 @@ def main_ours(args):
                                         "mma.sync temporal attention in the epilogue; no packed qkv tensor in HBM)",
                                         "achieved": t_flops / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0, "peak": peak_tf,
                                         "unit": "TFLOP/s", "frac": (t_flops / (t_ms / 1e3) / 1e12 / peak_tf) if t_ms > 0 else 0.0,
-                                        "launches": t_n, "ms_in_kernel_per_step": t_ms / args.steps},
+                                        "traffic": traffic_fused, "launches": t_n, "ms_in_kernel_per_step": t_ms / args.steps},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             # the step against the bf16 peak on EXECUTED FLOPs (never on skipped work); the reference-formulation figure
             # (784.1 GF per clip, counts the un-folded temporal_fc and the last block's dead patch-token work) beside it

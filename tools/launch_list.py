@@ -60,11 +60,15 @@ if big:
     # reported separately from the tensor-bound launches (bench.py: roofline vs roofline_hbm_gemm)
     def is_hbm(k):
         n = k["name"].replace("(int)", "").replace(" ", "")
-        return "gemm_bf16_tn_kernel<2,3,0,0>" in n and k.get("rd", 0.0) < 1.4e9
+        return "gemm_bf16_tn_kernel<2,3,0,0" in n and 0.5e9 < k.get("rd", 0.0) < 1.4e9
     hbm = [k for k in big if is_hbm(k)]
     ten = [k for k in big if not is_hbm(k)]
     tb = lambda ks: sum(k.get("rd", 0.0) + k.get("wr", 0.0) for k in ks) / max(len(ks), 1)
+    fused = [k for k in per.values() if "gemm_ln_tattn_kernel" in k["name"] and k.get("rd", 0.0) > 0.2e9]
+    ten = [k for k in ten if k.get("rd", 0.0) + k.get("wr", 0.0) > 0.5e9]      # full-batch launches only
     info = {
+        "fused_temporal_launches": len(fused),
+        "dram_bytes_per_launch_fused_temporal": tb(fused),
         "source": f"ncu launch list of `{cmd}` ({os.path.basename(dst)}): cold-cache, serialised; 2-CTA GEMM launches",
         "gemm_launches": len(ten),
         "dram_bytes_per_launch": tb(ten),
@@ -73,7 +77,8 @@ if big:
         "gemm_share_of_dvst_kernel_time": sum(k.get("us", 0.0) for k in big) / max(sum(k.get("us", 0.0) for k in dv), 1e-9),
         "algorithmic_bytes_note": "per launch the operands + outputs are read / written once (qkv: 308 MB A + 3.5 MB W + "
                                   "925 MB out; fc2 producer: 1 233 MB A + 616 MB residual in + 616 MB fp32 + 308 MB bf16 out; "
-                                  "K = 768 producers: 308 MB A + 616 MB in + 924 MB out = 1.85 GB)",
+                                  "K = 768 producers: 308 MB A + 616 MB in + 924 MB out = 1.85 GB; fused temporal qkv + attention: "
+                                  "308 MB xb in + 308 MB attention output = 0.62 GB - the 925 MB qkv tensor is never written)",
     }
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     json.dump(info, open(os.path.join(root, "profiles", "gemm_traffic.json"), "w"), indent=1)
