@@ -36,6 +36,7 @@ SIGNATURES = {
     "dvst_set_temporal_fusion": (None, [c_int]),
     "dvst_gemm_ln_temporal_attention": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_ll,
                                                 c_int, c_ll, c_void_p, c_ll, c_void_p]),
+    "dvst_temporal_tile_geometry": (c_int, [c_int, c_void_p, c_void_p]),
     "dvst_profile_enable": (None, [c_int]),
     "dvst_profile_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "dvst_create": (c_int, [c_void_p, c_void_p]),

@@ -101,6 +101,13 @@ int dvst_gemm_ln_temporal_attention(const void* xb, long long ldxb, const void* 
   return rc;
 }
 
+int dvst_temporal_tile_geometry(int T, int* rows_per_tile, int* key_block) {
+  if (rows_per_tile == nullptr || key_block == nullptr) return set_error("dvst_temporal_tile_geometry: null output");
+  if (temporal_tile_geometry(T, rows_per_tile, key_block) != 0)
+    return set_error("dvst_temporal_tile_geometry: T = %d is not covered (1 <= T <= 64)", T);
+  return 0;
+}
+
 int dvst_pair_loss(const float* student, long long lds, const float* teacher, long long ldt, const float* center,
                    float teacher_temp, float student_temp, int dim, int pairs, float* loss, void* stream) {
   if (dim <= 0 || pairs < 0) return set_error("dvst_pair_loss: bad dim %d / pairs %d", dim, pairs);

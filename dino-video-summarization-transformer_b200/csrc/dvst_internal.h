@@ -72,6 +72,7 @@ void set_producer_ring(int r);    // 5 (default) or 3 residual boxes per epilogu
 int launch_gemm_ln_tattn(const void* xb, long long ldxb, const void* w_perm, const float* bias_perm,
                          const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T,
                          long long clip_rows, void* out, long long ldo, cudaStream_t stream);
+int temporal_tile_geometry(int T, int* rows_per_tile, int* key_block);  // -1 when T is not covered
 void set_temporal_fusion(int on);  // 1 (default) use the fused kernel where the permuted tensors are registered
 int temporal_fusion();
 

@@ -486,18 +486,32 @@ int temporal_fusion() { return g_tattn_fusion; }
 // the sequences any 16-row query tile touches.  Returns false when T is not covered (T > 64).
 static bool tattn_geometry(int T, int* R_out, int* maxp_out) {
   if (T < 1 || T > 64) return false;
-  const int R = T <= 32 ? (BM / T) * T : T;
-  int span = 0;
-  for (int r0 = 0; r0 < R; r0 += 16) {
-    const int key0 = (r0 / T) * T;
-    const int last = r0 + 15 < R ? r0 + 15 : R - 1;
-    const int kend = (last / T + 1) * T;
-    if (kend - key0 > span) span = kend - key0;
+  // as many whole sequences as fit 128 rows, unless a 16-row query tile could then touch more than 64 rows of sequences
+  // (33 <= T <= 63): one sequence per tile there
+  for (int R = (BM / T) * T; R >= T; R = (R == T ? 0 : T)) {
+    int span = 0;
+    for (int r0 = 0; r0 < R; r0 += 16) {
+      const int key0 = (r0 / T) * T;
+      const int last = r0 + 15 < R ? r0 + 15 : R - 1;
+      const int kend = (last / T + 1) * T;
+      if (kend - key0 > span) span = kend - key0;
+    }
+    if (span <= 64) {
+      *R_out = R;
+      *maxp_out = span <= 16 ? 1 : (span <= 32 ? 2 : 4);
+      return true;
+    }
   }
-  if (span > 64) return false;
-  *R_out = R;
-  *maxp_out = span <= 16 ? 1 : (span <= 32 ? 2 : 4);
-  return true;
+  return false;
+}
+
+// exported for the host-logic tests (no GPU needed): geometry of the fused kernel for sequences of T rows
+int temporal_tile_geometry(int T, int* rows_per_tile, int* key_block) {
+  int R = 0, maxp = 0;
+  if (!tattn_geometry(T, &R, &maxp)) return -1;
+  *rows_per_tile = R;
+  *key_block = 16 * maxp;
+  return 0;
 }
 
 template <int MAXP>

@@ -198,6 +198,9 @@ int dvst_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw
 int dvst_gemm_ln_temporal_attention(const void* xb, long long ldxb, const void* w_perm, const float* bias_perm,
                                     const float* colsum_perm, const float* ln_stats, float ln_eps, long long M, int T,
                                     long long clip_rows, void* out, long long ldo, void* stream);
+/* Host-side geometry of that kernel (no device work): rows per CTA tile R = whole sequences (floor(128 / T) T, or T where a 16-row query tile would otherwise touch more than 64 rows)
+ * and the key-block size (16, 32 or 64) that holds every sequence a 16-row query tile touches; DVST_ERR for T outside 1..64. */
+int dvst_temporal_tile_geometry(int T, int* rows_per_tile, int* key_block);
 /* nn.LayerNorm(768, eps) over M rows of fp32 (models/timesformer.py:99,105,112,245).  out_kind as above. */
 int dvst_layernorm768(const float* x, long long ldx, const float* gamma, const float* beta, void* out, long long ldo,
                       int out_kind, long long lo_off, long long M, float eps, void* stream);

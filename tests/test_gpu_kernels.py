@@ -548,7 +548,7 @@ def test_attention_high_precision_tcgen05(dev, mode, B, T, N, impl):
 # ---- temporal half of a divided block in one kernel: deferred-LayerNorm qkv GEMM + temporal attention out of shared memory
 @pytest.mark.parametrize("T,n_seq,clip_seqs", [(16, 313, 0), (16, 8, 0), (32, 77, 0), (64, 9, 0), (8, 401, 0), (4, 1000, 0),
                                                (1, 300, 0), (30, 131, 0), (3, 1571, 0), (5, 52, 0), (17, 40, 0), (48, 7, 0),
-                                               (2, 64, 0), (30, 196 * 3, 196), (3, 196 * 7, 196), (16, 196 * 3, 196),
+                                               (2, 64, 0), (64, 33, 0), (48, 21, 0), (40, 9, 0), (30, 196 * 3, 196), (3, 196 * 7, 196), (16, 196 * 3, 196),
                                                (5, 36 * 4, 36), (8, 49 * 5, 49)])
 def test_fused_temporal_qkv_attention(dev, T, n_seq, clip_seqs):
     """dvst_gemm_ln_temporal_attention vs the two-kernel form (dvst_gemm_bf16_ln consumer -> dvst_attention mode 0) and vs

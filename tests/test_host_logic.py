@@ -202,3 +202,31 @@ def test_short_video_clips_match_reference_loader_golden(golden_dir):
         si, ti = short_video_clips(F, 3)
         assert O.short_video_clips(F, 3) == (si, ti) and len(W[str(F)]) == F
         assert all(p["student"] == si and p["teacher"] == ti for p in W[str(F)])
+
+
+def test_fused_temporal_kernel_tile_geometry():
+    """Host logic of csrc/gemm_tattn_sm100.cu (no device work): for every T <= 64 a CTA tile holds whole sequences, and the
+    key block of every 16-row query tile (first row of the first sequence it touches, moved down when it would pass row 128)
+    contains every sequence those 16 rows belong to - the property the in-kernel sequence mask relies on."""
+    import ctypes
+    from dvst_b200 import _lib
+    L = _lib.lib()
+    for T in range(1, 65):
+        R, KB = ctypes.c_int(), ctypes.c_int()
+        assert L.dvst_temporal_tile_geometry(T, ctypes.byref(R), ctypes.byref(KB)) == 0
+        R, KB = R.value, KB.value
+        assert R % T == 0 and 0 < R <= 128 and KB in (16, 32, 64)
+        R0 = (128 // T) * T      # as many whole sequences as fit, unless a query tile would then span more than 64 rows
+        span0 = max(((min(r0 + 15, R0 - 1) // T) + 1) * T - (r0 // T) * T for r0 in range(0, R0, 16))
+        assert R == (R0 if span0 <= 64 else T)
+        for r0 in range(0, R, 16):
+            key0 = min((r0 // T) * T, 128 - KB)
+            for r in range(r0, min(r0 + 16, R)):
+                s0 = (r // T) * T
+                assert key0 <= s0 and s0 + T <= key0 + KB, (T, r0, r)
+        if T & (T - 1) == 0:
+            assert R == 128 and KB == max(16, T)       # power-of-two T: no masking needed from T = 16 up
+    R, KB = ctypes.c_int(), ctypes.c_int()
+    for T in (0, 65, 1000):
+        assert L.dvst_temporal_tile_geometry(T, ctypes.byref(R), ctypes.byref(KB)) != 0
+        assert b"not covered" in L.dvst_last_error()
