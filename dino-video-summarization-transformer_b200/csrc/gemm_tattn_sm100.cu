@@ -70,19 +70,6 @@ constexpr int NUM_OBOX = ATT_WARPS;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + ACC_STAGES * QKV_BYTES + NUM_OBOX * OBOX_BYTES + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
-__device__ __forceinline__ float4 ldg_f4_stream(const float4* p) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float4 ldg_f4_keep(const float4* p) {
-  float4 r;
-  asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
-      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-
 struct TAttnParams {
   int M;             // patch-token rows
   int T, R;          // frames per sequence, rows per CTA tile (whole sequences)

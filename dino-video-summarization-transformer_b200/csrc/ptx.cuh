@@ -74,6 +74,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
 
+// Read-only global loads with L1 policies.  The epilogues re-read a few KiB of per-column constants (bias, folded-LayerNorm
+// column sums) for every tile and stream per-row statistics once; with ~225 KiB of the SM's 256 KiB given to shared memory
+// the L1 that is left (~26 KiB) holds the constants only if the streams do not allocate in it.  (Used by the fused temporal
+// kernel, where it is neutral; in the plain GEMM epilogues these policies measured SLOWER than ld.global.nc defaults - fc1
+// deferred-LN + GELU 0.876 -> 0.955 ms sustained - and are not used there.)
+__device__ __forceinline__ float4 ldg_f4_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_f4_keep(const float4* p) {
+  float4 r;
+  asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
 // thread-block clusters (cta_group::2 CTA pairs)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
