@@ -663,8 +663,8 @@ int num_sms() {
   return n;
 }
 
-static int g_producer_ring = 5;
-void set_producer_ring(int r) { g_producer_ring = r > 3 ? 5 : 3; }
+static int g_producer_ring = 5;       // 3: never the deep ring, 5: for K <= 1024, 6: for every K (experiment)
+void set_producer_ring(int r) { g_producer_ring = r <= 3 ? 3 : (r >= 6 ? 6 : 5); }
 static int g_gemm_cta_group = 2;
 void set_gemm_cta_group(int cg) { g_gemm_cta_group = cg == 1 ? 1 : 2; }
 
@@ -760,7 +760,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.out_kind == 3) {
     if (!cg2) return launch_gemm_impl<1, 3, 0, 0>(g, stream);
     // short K: bound by the residual stream - deeper residual prefetch, one operand stage fewer
-    return g.K <= 1024 && g_producer_ring > 3 ? launch_gemm_impl<2, 3, 0, 0, 5>(g, stream) : launch_gemm_impl<2, 3, 0, 0>(g, stream);
+    return (g.K <= 1024 && g_producer_ring > 3) || g_producer_ring == 6 ? launch_gemm_impl<2, 3, 0, 0, 5>(g, stream)
+                                                                         : launch_gemm_impl<2, 3, 0, 0>(g, stream);
   }
 #define DVST_GEMM_CASE(OUT, ACT)                                                                   \
   if (g.out_kind == OUT && g.act == ACT)                                                           \

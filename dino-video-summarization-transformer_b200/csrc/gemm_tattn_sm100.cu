@@ -8,29 +8,31 @@
 //
 //   * the weight rows are permuted at pack time so that one 192-column N tile is exactly [q_h | k_h | v_h] of ONE head;
 //   * an M tile of the resident (b, n, t) row order is R = floor(128 / T) * T consecutive token rows = a whole number of
-//     (b, n) sequences (T = 16: 8 sequences, T = 30: 4, T = 3: 42), so a (128-row, 192-column) accumulator tile holds
-//     everything the temporal attention of those sequences and that head needs;
-//   * the epilogue warps apply the folded LayerNorm (gemm_sm100.cu), round q / k / v to bf16 into a swizzled staging tile in
-//     SHARED MEMORY, run the attention of their 16 query rows with mma.sync m16n8k16 straight out of that tile (exactly the
-//     arithmetic of temporal_attention_kernel, attention.cu - for T in {16, 32, 64} the results are bit-identical to the
-//     two-kernel form) and TMA-store the 16 x 64 output box into the A operand of the temporal proj*fc GEMM.
+//     (b, n) sequences (T = 16: 8 sequences, T = 30: 4, T = 3: 42; tattn_geometry below), optionally tiled clip by clip, so a
+//     (128-row, 192-column) accumulator tile holds everything the temporal attention of those sequences and that head needs;
+//   * drain warps apply the folded LayerNorm (gemm_sm100.cu) and round q / k / v to bf16 into a swizzled staging tile in
+//     SHARED MEMORY; attention warps run the attention of 16 query rows each with mma.sync m16n8k16 straight out of that
+//     tile (exactly the arithmetic of temporal_attention_kernel, attention.cu - for power-of-two T the results are
+//     bit-identical to the two-kernel form) and TMA-store the 16 x 64 output box into the A operand of the temporal
+//     proj*fc GEMM.
 //
 // Per token and block this removes the 4 608-byte qkv write and read (the qkv GEMM is tensor bound, the attention kernel
 // HBM bound: 1.85 GB per cfg2 launch pair) and one launch; the main loop is the 2-CTA tcgen05 pipeline of gemm_sm100.cu
 // with 256 x 192 tiles (TMEM: 2 x 192 of 512 columns).
 //
-// Warp roles (512 threads, CTA pairs, persistent): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM
-// allocator, warps 4..11 drain, warps 12..15 attention.  Per tile and CTA (its own 128 accumulator rows):
+// Warp roles (640 threads, CTA pairs, persistent): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM
+// allocator, warps 4..11 drain, warps 12..19 attention.  Per tile and CTA (its own 128 accumulator rows):
 //   drain      warp e: TMEM lane quarter e & 3, columns [96 (e >> 2), +96) -> LayerNorm fold -> bf16 -> staging buffer
 //              (tile parity) [128 rows][q 128 B | k 128 B | v 128 B], 16-byte chunks XOR-swizzled with (row & 7); the TMEM
 //              stage goes back to the MMA warp, the staging buffer to the attention warps (mbarrier)
-//   attention  warp w: query rows [32 w, 32 w + 32) as two 16-row mma.sync tiles against the key rows of the sequences
-//              those rows belong to (a 16-, 32- or 64-key block; keys of other sequences masked), output -> swizzled
-//              16 x 128 B box -> TMA store; staging buffer handed back
+//   attention  warp w: query rows [16 w, 16 w + 16) as one mma.sync tile against the key rows of the sequences those rows
+//              belong to (a 16-, 32- or 64-key block; keys of other sequences masked), output -> swizzled 16 x 128 B box ->
+//              TMA store; staging buffer handed back
 // The two roles overlap (double-buffered staging): the legacy HMMA instructions of the attention only issue in the gaps
 // between the main loop's tcgen05.mma instructions (ncu of the first version, where the drain warps also ran the attention:
 // 42 % of their time waiting at HMMA, epilogue-bound at 0.73 ms per cfg2 launch) - dedicated warps take that wait off the
-// accumulator-drain path.
+// accumulator-drain path (4 warps: 0.63 ms, 8 warps: 0.60 ms; 0.48 ms with the attention compiled out,
+// -DDVST_TATTN_EXP_NO_ATTENTION).
 #include "attn_sm100_common.cuh"
 #include "dvst_internal.h"
 #include "mma_sync.cuh"
