@@ -10,8 +10,9 @@ backbone forward, the DINO projection head and the fused centred / sharpened cro
 pairs formed by (clip 2i, clip 2i+1); weak scaling (every rank scores its own 64 videos, no data-path collective; the
 32 per-rank losses are all-gathered).  `value` is timed with inputs resident in HBM; `e2e` goes through the public
 module API from pinned HOST buffers: the step's 1 024 decoded frames are uploaded as uint8 (what a decoder produces),
-normalised on the device (dvst_preprocess_u8), windowed into clips by index (dvst_forward_windows), and the losses are
-read back - H2D and D2H inside the timed region.
+normalised, windowed into clips by index and cut into patch rows in one pass on the device (dvst_forward_windows_u8:
+the loader front half inside the patch extraction, bit-identical to dvst_preprocess_u8 + dvst_forward_windows), and the
+losses are read back - H2D and D2H inside the timed region.
 
 Beside the headline the line carries
   * `parity`      - the GPU step's features / loss for two cfg2 clips against the CPU arm's (the run FAILS above 2e-2 / 1e-3),
@@ -75,7 +76,7 @@ def workload_config(n_gpus):
             "l2_policy": "inputs exceed L2 (616 MB of clips per step vs 126 MB L2); activations 3 GB per step",
             "precision": "bf16 operands, fp32 accumulate / residual / LayerNorm / softmax",
             "e2e_input": "uint8 decoded frames [1024,224,224,3] from pinned host memory (154 MB per step), normalised on "
-                         "the device"}
+                         "the device inside the patch extraction (dvst_forward_windows_u8)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -355,8 +356,8 @@ def main_ours(args):
     import dvst_b200  # noqa: F401
     from functools import partial
     from dvst_b200 import _lib
-    from dvst_b200.dino_similarity import (DINOLoss, HeadScorer, _forward_windows, preprocess_frames,
-                                           score_video_device, score_videos_device)
+    from dvst_b200.dino_similarity import (DINOLoss, HeadScorer, forward_windows_u8, score_video_device,
+                                           score_videos_device)
     from dvst_b200.models.timesformer import VisionTransformer
     from dvst_b200.testing import synth_backbone_state_dict, synth_clips, synth_head_state_dict, synth_video
     from dvst_b200.vision_transformer import DINOHead
@@ -453,12 +454,12 @@ def main_ours(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
     host_loss = [torch.empty(world * P if world > 1 else P, dtype=torch.float32).pin_memory() for _ in range(2)]
-    starts = list(range(0, n_frames, T))
+    starts_dev = torch.arange(0, n_frames, T, dtype=torch.int32, device=dev)
 
     def step_u8(u8):
         with torch.no_grad():
-            frames = preprocess_frames(u8, 1)                       # [1024,3,224,224] fp32, normalised (one kernel)
-            return finish(_forward_windows(model, frames, starts, T, B_PER_GPU))
+            # decoded uint8 frames -> normalise + crop + clip windows + patch rows in one pass (dvst_forward_windows_u8)
+            return finish(forward_windows_u8(model, u8, starts_dev, T, B_PER_GPU, sampling_rate=1))
 
     def e2e_run(n_steps):
         results = []

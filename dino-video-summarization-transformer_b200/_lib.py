@@ -52,6 +52,8 @@ SIGNATURES = {
                                c_void_p]),
     "dvst_forward_windows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_ll, c_void_p]),
+    "dvst_forward_windows_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                        c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p]),
     "dvst_pair_loss_indexed": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_float, c_float,
                                        c_int, c_int, c_void_p, c_void_p]),
     "dvst_head_loss_scratch_bytes": (c_ll, [c_int]),

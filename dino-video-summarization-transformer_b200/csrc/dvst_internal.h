@@ -88,6 +88,10 @@ int launch_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, 
 int launch_row_offsets768(const float* stats, float* xoff, long long M, cudaStream_t st);
 int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,
                     const int* starts, cudaStream_t st);
+// patch rows straight from decoded uint8 frames [n, Hf, Wf, 3] (normalise + centre crop + window gather + im2col in one pass)
+int launch_im2col16_u8(const uint8_t* video, int Hf, int Wf, int rate, const float* mean3, const float* std3, int crop,
+                       void* out, long long ldo, int split, long long lo_off, int B, int T, const int* starts,
+                       cudaStream_t st);
 int launch_cast_bf16(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off, long long M,
                      int cols, cudaStream_t st);
 int launch_l2norm_rows(const float* in, long long ldi, void* out, long long ldo, int split, long long lo_off,

@@ -155,6 +155,43 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__
   }
 }
 
+// The same patch rows straight from DECODED frames: video uint8 [n_frames, Hf, Wf, 3]; clip b = the T sampled frames
+// (every rate-th decoded frame) starting at sampled index starts[b]; pixel -> / 255, - mean, / std with the loader's three
+// separately rounded fp32 operations (data_utils.py:308-325, = preprocess_u8_kernel), centre crop at (y0, x0)
+// (transform.py:228-229).  Replaces preprocess_u8_kernel + im2col16_kernel when every frame is used once (clips cut from a
+// stream of frames): the normalised fp32 frames (4 x the uint8 bytes, written and read back) never exist.
+struct U8Norm { float m[3], s[3]; };
+__global__ void __launch_bounds__(256) im2col16_u8_kernel(const uint8_t* __restrict__ video, __nv_bfloat16* __restrict__ out,
+                                                          long long ldo, int split, long long lo_off, int B, int T, int Hf,
+                                                          int Wf, int rate, int y0, int x0, int gh, int gw,
+                                                          const int* __restrict__ starts, const U8Norm nrm) {
+  const long long total = static_cast<long long>(B) * gh * gw * T * 96;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunk = static_cast<int>(idx % 96);
+  const long long row = idx / 96;
+  const int t = static_cast<int>(row % T);
+  const long long bn = row / T;
+  const int n = static_cast<int>(bn % (gh * gw));
+  const int b = static_cast<int>(bn / (gh * gw));
+  const int c = chunk / 32, rem = chunk % 32, ky = rem / 2, kx0 = (rem % 2) * 8;
+  const int py = n / gw, px = n % gw;
+  const long long f = static_cast<long long>(__ldg(starts + b) + t) * rate;
+  const uint8_t* src = video + ((f * Hf + (y0 + py * 16 + ky)) * Wf + (x0 + px * 16 + kx0)) * 3 + c;
+  const float mean = nrm.m[c], sd = nrm.s[c];
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    v[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(__ldg(src + 3 * i)), 255.0f), mean), sd);
+  __nv_bfloat16* o = out + row * ldo + chunk * 8;
+  *reinterpret_cast<uint4*>(o) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+  if (split) {
+    *reinterpret_cast<uint4*>(o + lo_off) =
+        make_uint4(pack2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1])), pack2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3])),
+                   pack2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5])), pack2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7])));
+  }
+}
+
 // emb[n*T + t, :] = pos_embed[1 + pi(n)] + time_embed[tau(t)]: the additive embedding of every patch token
 // (timesformer.py:288-323), with the reference's nearest-neighbour resizes (F.interpolate(mode='nearest'), :292-303
 // and :314-318) evaluated exactly like ATen: src = min(floor(dst * float(src_len)/float(dst_len)), src_len - 1).
@@ -381,6 +418,25 @@ int launch_im2col16(const float* x, void* out, long long ldo, int split, long lo
       x, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, H, W, gh, gw, starts);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("im2col launch failed");
+}
+
+int launch_im2col16_u8(const uint8_t* video, int Hf, int Wf, int rate, const float* mean3, const float* std3, int crop,
+                       void* out, long long ldo, int split, long long lo_off, int B, int T, const int* starts,
+                       cudaStream_t st) {
+  if (crop % 16 || crop <= 0 || Hf < crop || Wf < crop || rate <= 0)
+    return set_error("im2col_u8: bad crop %d / rate %d for %dx%d frames", crop, rate, Hf, Wf);
+  const int gh = crop / 16, gw = crop / 16;
+  const long long total = static_cast<long long>(B) * gh * gw * T * 96;
+  if (total == 0) return 0;
+  U8Norm nrm;
+  for (int i = 0; i < 3; ++i) { nrm.m[i] = mean3[i]; nrm.s[i] = std3[i]; }
+  // ceil((H - crop) / 2) like transform.py:228-229 (math.ceil of a float division), as in launch_preprocess_u8
+  const int y0 = (Hf - crop + 1) / 2, x0 = (Wf - crop + 1) / 2;
+  ProfScope prof(PROF_ELEMENTWISE, static_cast<double>(total) * 8 * (1.0 + (split ? 4.0 : 2.0)), st);
+  im2col16_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      video, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, Hf, Wf, rate, y0, x0, gh, gw, starts, nrm);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : set_error("im2col_u8 launch failed");
 }
 
 int launch_embed_table(const float* pos, int P, const float* time_embed, int T0, float* out, int gh, int gw, int T,

@@ -226,9 +226,17 @@ long long dvst_workspace_bytes(const dvst_model* h, int B, int T, int H, int W) 
   return static_cast<long long>(carve(*m, nullptr, cb, T, H / 16, W / 16).total);
 }
 
+// Decoded uint8 frames as the input of the patch embedding (dvst_forward_windows_u8): x_in is then null
+struct U8Source {
+  const uint8_t* video = nullptr;
+  int Hf = 0, Wf = 0, rate = 1;
+  float mean[3] = {0, 0, 0}, std[3] = {1, 1, 1};
+};
+
 // get_all: 0 = CLS features, 1 = every token, 2 = attention map of the last block's spatial attention (get_attn)
 static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
-                        int get_all, void* workspace, long long workspace_bytes, void* stream);
+                        int get_all, void* workspace, long long workspace_bytes, void* stream,
+                        const U8Source* u8 = nullptr);
 
 int dvst_forward_features(dvst_model* h, const float* x_in, int B, int T, int H, int W, float* out, int get_all,
                           void* workspace, long long workspace_bytes, void* stream) {
@@ -250,11 +258,26 @@ int dvst_forward_windows(dvst_model* h, const float* frames, int F, const int* s
   return forward_impl(h, frames, starts, n_clips, T, H, W, out, 0, workspace, workspace_bytes, stream);
 }
 
+int dvst_forward_windows_u8(dvst_model* h, const unsigned char* video, int n_frames, int Hf, int Wf, int sampling_rate,
+                            const float* mean3, const float* std3, int crop, const int* starts, int n_clips, int T,
+                            float* out, void* workspace, long long workspace_bytes, void* stream) {
+  if (video == nullptr || mean3 == nullptr || std3 == nullptr || starts == nullptr)
+    return set_error("dvst_forward_windows_u8: null argument");
+  if (sampling_rate <= 0 || crop <= 0 || crop % 16 || Hf < crop || Wf < crop)
+    return set_error("dvst_forward_windows_u8: bad sampling rate %d / crop %d for %dx%d frames", sampling_rate, crop, Hf, Wf);
+  const int F = (n_frames + sampling_rate - 1) / sampling_rate;
+  if (F < T) return set_error("dvst_forward_windows_u8: video has %d sampled frames, window needs %d", F, T);
+  U8Source u8;
+  u8.video = video; u8.Hf = Hf; u8.Wf = Wf; u8.rate = sampling_rate;
+  for (int i = 0; i < 3; ++i) { u8.mean[i] = mean3[i]; u8.std[i] = std3[i]; }
+  return forward_impl(h, nullptr, starts, n_clips, T, crop, crop, out, 0, workspace, workspace_bytes, stream, &u8);
+}
+
 static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
-                         int get_all, void* workspace, long long workspace_bytes, void* stream);
+                         int get_all, void* workspace, long long workspace_bytes, void* stream, const U8Source* u8);
 
 static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
-                        int get_all, void* workspace, long long workspace_bytes, void* stream) {
+                        int get_all, void* workspace, long long workspace_bytes, void* stream, const U8Source* u8) {
   if (h == nullptr) return set_error("dvst_forward_features: null handle");
   if (B <= 0 || T <= 0 || H < 16 || W < 16) return set_error("dvst_forward_features: bad shape");
   const Model* m = reinterpret_cast<const Model*>(h);
@@ -263,24 +286,24 @@ static int forward_impl(dvst_model* h, const float* x_in, const int* starts, int
   const long long out_rows = get_all == 1 ? 1 + (m->cfg.attention_type == DVST_ATTN_SPACE_ONLY ? N : N * T) : 1;
   for (int b0 = 0; b0 < B; b0 += cb) {
     const int nb = B - b0 < cb ? B - b0 : cb;
-    const float* xin = starts ? x_in : x_in + static_cast<long long>(b0) * 3 * T * H * W;
+    const float* xin = (starts || u8) ? x_in : x_in + static_cast<long long>(b0) * 3 * T * H * W;
     float* o = get_all == 2 ? out + static_cast<long long>(b0) * T * 12 * (N + 1) * (N + 1) : out + b0 * out_rows * D;
     const int rc = forward_chunk(h, xin, starts ? starts + b0 : nullptr, nb, T, H, W, o, get_all, workspace,
-                                 workspace_bytes, stream);
+                                 workspace_bytes, stream, u8);
     if (rc != 0) return rc;
   }
   return 0;
 }
 
 static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, int B, int T, int H, int W, float* out,
-                         int get_all, void* workspace, long long workspace_bytes, void* stream) {
+                         int get_all, void* workspace, long long workspace_bytes, void* stream, const U8Source* u8) {
   if (h == nullptr) return set_error("dvst_forward_features: null handle");
   Model* m = reinterpret_cast<Model*>(h);
   if (!m->finalized) return set_error("dvst_forward_features: weights not finalized");
   if (B <= 0 || T <= 0) return set_error("dvst_forward_features: bad batch %d / frames %d", B, T);
   if (H % 16 || W % 16 || H < 16 || W < 16)
     return set_error("dvst_forward_features: H, W must be multiples of the patch size 16 (got %dx%d)", H, W);
-  if ((reinterpret_cast<uintptr_t>(x_in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+  if ((u8 == nullptr && (reinterpret_cast<uintptr_t>(x_in) & 15)) || (reinterpret_cast<uintptr_t>(out) & 15) ||
       (reinterpret_cast<uintptr_t>(workspace) & 1023))
     return set_error("dvst_forward_features: x/out must be 16-byte and workspace 1024-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -341,7 +364,10 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
 
   // ---- patch embedding + positional / temporal embedding (timesformer.py:203-209,287-323) ----
   DVST_TRY(launch_embed_table(m->pos, m->cfg.pos_grid, m->time_embed, m->cfg.num_frames, w.emb, gh, gw, T, st));
-  DVST_TRY(launch_im2col16(x_in, w.a, lda, split, D, B, T, H, W, starts, st));
+  if (u8 != nullptr)
+    DVST_TRY(launch_im2col16_u8(u8->video, u8->Hf, u8->Wf, u8->rate, u8->mean, u8->std, H, w.a, lda, split, D, B, T, starts, st));
+  else
+    DVST_TRY(launch_im2col16(x_in, w.a, lda, split, D, B, T, H, W, starts, st));
   DVST_TRY(launch_tile_rows768(w.emb, N * T, w.x, Mt, st));  // x[b, n, t] = pos + time; the GEMM accumulates onto it
   if (fl) {
     // offsets start at 0 for the patch rows (the embedded tokens are centred well enough); the CLS rows get their exact mean

@@ -236,6 +236,48 @@ def _forward_windows(model, frames, starts, T, max_clips, out=None, ws="_workspa
     return out
 
 
+def forward_windows_u8(model, video_uint8, starts, T, max_clips=64, sampling_rate=1, mean=(0.45, 0.45, 0.45),
+                       std=(0.225, 0.225, 0.225), crop_size=224, out=None, ws="_workspace"):
+    """Features [n, 768] of T-frame windows cut straight from DECODED frames (uint8 [n_frames,H,W,3] on the device): the
+    loader front half (sub-sampling, / 255, mean / std, centre crop - datasets_custom/dino_loss_loader.py:80-92) is applied
+    inside the patch extraction (dvst_forward_windows_u8), bit-identical to preprocess_frames() + _forward_windows() without
+    the normalised fp32 frames in between.  `starts` index the sampled frame axis."""
+    if not (video_uint8.is_cuda and video_uint8.dtype == torch.uint8 and video_uint8.dim() == 4
+            and video_uint8.shape[3] == 3):
+        raise _lib.DvstError("forward_windows_u8: expected a CUDA uint8 tensor [n,H,W,3] (decoded frames); dvst_b200 runs on "
+                             "CUDA (sm_100a) only - there is no CPU fallback")
+    import ctypes
+    L = _lib.lib()
+    dev = video_uint8.device
+    model._ensure_packed(dev)
+    v = video_uint8.contiguous()
+    n_frames, hf, wf = v.shape[0], v.shape[1], v.shape[2]
+    if torch.is_tensor(starts):
+        if starts.dtype != torch.int32 or starts.device != dev:
+            raise ValueError("window starts must be an int32 tensor on the frames' device")
+        starts_t = starts.contiguous()
+    else:
+        starts_t = torch.tensor(starts, dtype=torch.int32, device=dev)
+    n = starts_t.numel()
+    if out is None:
+        out = torch.empty(n, model.embed_dim, dtype=torch.float32, device=dev)
+    m3 = (ctypes.c_float * 3)(*[float(x) for x in mean])
+    s3 = (ctypes.c_float * 3)(*[float(x) for x in std])
+    with torch.cuda.device(dev):
+        for c0 in range(0, n, max_clips):
+            nb = min(max_clips, n - c0)
+            need = L.dvst_workspace_bytes(model._handle, nb, T, crop_size, crop_size)
+            buf = getattr(model, ws, None)
+            if buf is None or buf.numel() < need or buf.device != dev:
+                setattr(model, ws, None)
+                buf = torch.empty(need, dtype=torch.uint8, device=dev)
+                setattr(model, ws, buf)
+            _lib.check(L.dvst_forward_windows_u8(model._handle, _lib.ptr(v), n_frames, hf, wf, sampling_rate, m3, s3,
+                                                 crop_size, _lib.ptr(starts_t[c0:]), nb, T, _lib.ptr(out[c0:]),
+                                                 _lib.ptr(buf), buf.numel(), _lib.cur_stream()))
+    return out
+
+
 def plan_windows(lengths, local_clip_size, global_clip_size, device):
     """dvst_plan_windows: the loader's window rule for a batch of videos (concatenated along the frame axis) as device
     index arrays.  Returns (s_starts, t_starts, s_idx, t_idx, groups) with groups = [(G, n_windows, first_row), ...]

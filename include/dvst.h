@@ -117,6 +117,16 @@ int dvst_forward_attention_map(dvst_model* m, const float* x, int B, int T, int 
 int dvst_forward_windows(dvst_model* m, const float* frames, int F, const int* starts, int n_clips, int T, int H,
                          int W, float* out, void* workspace, long long workspace_bytes, void* stream);
 
+/* The same straight from DECODED frames: `video` uint8 [n_frames, Hf, Wf, 3] (device); the frame axis of `starts` is the
+ * SAMPLED one (every sampling_rate-th decoded frame, datasets_custom/dino_loss_loader.py:80-92); normalisation (/ 255, - mean,
+ * / std: the loader's three fp32 operations, data_utils.py:308-325), centre crop to crop x crop (transform.py:228-229), window
+ * gather and patch extraction happen in ONE pass - bit-identical to dvst_preprocess_u8 followed by dvst_forward_windows, without
+ * the normalised fp32 frames in between.  For clips cut from a stream of frames (every frame used once); whole-video scoring,
+ * where each frame is reused by ~33 windows, normalises once with dvst_preprocess_u8.  mean3 / std3 are HOST pointers. */
+int dvst_forward_windows_u8(dvst_model* m, const unsigned char* video, int n_frames, int Hf, int Wf, int sampling_rate,
+                            const float* mean3, const float* std3, int crop, const int* starts, int n_clips, int T,
+                            float* out, void* workspace, long long workspace_bytes, void* stream);
+
 /* Scoring DINOLoss.forward for `pairs` rows at once - dino_similarity.py:129-135:
  *   loss[p] = sum_j -softmax((t[p]-center)/teacher_temp)_j * log_softmax(s[p]/student_temp)_j
  * student / teacher fp32 [pairs, dim] (row strides lds / ldt), center fp32 [dim] or NULL (zeros), loss fp32 [pairs]. */

@@ -600,3 +600,30 @@ def test_training_forward_has_a_pytorch_backward(dev):
             worst = max(worst, ((g - v.grad).norm() / (v.grad.norm() + 1e-12)).item())
     # the backward runs on the kernels' student output (bf16-level forward difference feeds softmax(s / tau)): a few 1e-3
     assert worst < 2e-2, worst
+
+
+@pytest.mark.parametrize("prec", ["bf16", "high"])
+def test_windows_from_decoded_uint8_frames_equal_the_two_step_path(dev, prec):
+    """dvst_forward_windows_u8 (sub-sampling, / 255, mean / std, centre crop, window gather and patch extraction in one
+    pass over the decoded uint8 frames - datasets_custom/dino_loss_loader.py:80-92,126-171 + models/timesformer.py:201-208)
+    gives the same BITS as preprocess_frames() followed by the window forward, and agrees with the CPU oracle of the loader
+    front half + backbone."""
+    from dvst_b200.dino_similarity import _forward_windows, forward_windows_u8
+    m = build(dev, 3, 2, "divided_space_time", prec)
+    g = torch.Generator().manual_seed(77)
+    for (n_frames, hf, wf, rate, crop, T, starts) in [(22, 240, 320, 2, 224, 4, [0, 3, 7, 2]), (9, 224, 224, 1, 224, 3, [0, 6]),
+                                                      (16, 130, 171, 4, 96, 2, [0, 1, 2]), (8, 256, 256, 1, 224, 8, [0])]:
+        raw = torch.randint(0, 256, (n_frames, hf, wf, 3), generator=g, dtype=torch.uint8)
+        with torch.no_grad():
+            frames = preprocess_frames(raw.to(dev), rate, crop_size=crop)
+            two = _forward_windows(m, frames, starts, T, 3)
+            one = forward_windows_u8(m, raw.to(dev), starts, T, 3, sampling_rate=rate, crop_size=crop)
+        assert torch.equal(one, two)
+    # against the CPU statement of the loader front half + the fp32 oracle backbone (last case: one 8-frame clip)
+    sd = synth_backbone_state_dict(3, depth=2, num_frames=8)
+    ref = O.forward_features(sd, O.preprocess_frames(raw, 1, crop_size=224).permute(1, 0, 2, 3)[None])
+    assert _rel(one, ref) < (FEAT_TOL if prec == "bf16" else 1e-4)
+    with pytest.raises(_lib.DvstError):
+        forward_windows_u8(m, raw, [0], 8)                       # CPU input: no fallback
+    with pytest.raises(_lib.DvstError):
+        forward_windows_u8(m, raw.to(dev), [0], 9)               # window longer than the video
