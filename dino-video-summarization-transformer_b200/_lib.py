@@ -30,6 +30,7 @@ SIGNATURES = {
                                c_void_p, c_ll, c_int, c_ll, c_int, c_void_p]),
     "dvst_set_gemm_cta_group": (None, [c_int]),
     "dvst_set_producer_ring": (None, [c_int]),
+    "dvst_set_pdl": (None, [c_int]),
     "dvst_set_attention_impl": (None, [c_int]),
     "dvst_set_chunk_rows": (None, [c_ll]),
     "dvst_set_ln_fusion": (None, [c_int]),
@@ -104,6 +105,9 @@ def lib():
         # experiment switches (A/B runs of bench.py on one box): DVST_LN_FUSION=0 forces the stand-alone LayerNorm
         if os.environ.get("DVST_LN_FUSION") == "0":
             l.dvst_set_ln_fusion(0)
+        # DVST_PDL=1: programmatic dependent launch for the hot-path kernels (off by default)
+        if os.environ.get("DVST_PDL") == "1":
+            l.dvst_set_pdl(1)
         if os.environ.get("DVST_PRODUCER_RING"):
             l.dvst_set_producer_ring(int(os.environ["DVST_PRODUCER_RING"]))
         # DVST_TATTN_FUSION=0: qkv GEMM + temporal attention as two kernels (the round-1 form)

@@ -22,6 +22,9 @@ int set_error(const char* fmt, ...) {
   return DVST_ERR;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static int g_pdl = 0;   // measured: neutral on the cfg2 step, -4 % on two-stream whole-video scoring, +11 % single-stream
+int pdl_enabled() { return g_pdl; }
+void set_pdl(int on) { g_pdl = on != 0 ? 1 : 0; }
 
 struct ProfRec { int kind; double work; cudaEvent_t e0, e1; };
 static bool g_prof = false;
@@ -59,6 +62,7 @@ const char* dvst_last_error(void) { return g_err; }
 long long dvst_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int dvst_abi_version(void) { return DVST_ABI_VERSION; }
 void dvst_set_gemm_cta_group(int cg) { set_gemm_cta_group(cg); }
+void dvst_set_pdl(int on) { set_pdl(on); }
 void dvst_set_producer_ring(int r) { set_producer_ring(r); }
 void dvst_set_attention_impl(int impl) { set_attention_impl(impl); }
 

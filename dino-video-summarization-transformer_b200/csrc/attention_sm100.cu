@@ -363,6 +363,8 @@ spatial_attention_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, const _
 
 // Exact fp32 recomputation of the rows the one-pass softmax could not normalise: one warp per (problem, row).
 __global__ void __launch_bounds__(128) attention_fixup_kernel(const SpParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int n_fix = *p.fix_count;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -518,7 +520,7 @@ int launch_spatial_attention_sm100(const void* qkv, long long ld, void* out, lon
     int rc2 = g_attention_impl == 1 ? launch_spatial_attention_split_sm100(p, tmIn, tmOutA, tmOutB, grid, st) : 1;
     if (rc2 != 0 && rc2 != 1) return rc2;
     if (rc2 == 1) spatial_attention_sm100_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p);
-    attention_fixup_kernel<<<grid < 64 ? grid : 64, 128, 0, st>>>(p);
+    launch_kernel_pdl(attention_fixup_kernel, dim3(grid < 64 ? grid : 64), dim3(128), 0, st, p);
     count_launch();
   } else {
     spatial_attention_sm100_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p);

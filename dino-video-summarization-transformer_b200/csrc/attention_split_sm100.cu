@@ -170,6 +170,8 @@ spatial_attention_split_sm100_kernel(const __grid_constant__ CUtensorMap tmIn, c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // the prologue above touched shared memory and TMEM only
+  pdl_launch_dependents();
 #ifdef DVST_SP2_TIMING
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -575,10 +577,14 @@ int launch_spatial_attention_split_sm100(const SpParams& p, const CUtensorMap& t
     if (e != cudaSuccess) return set_error("attention(split sm100) attr: %s", cudaGetErrorString(e));
     cur = smem;
   }
+  cudaError_t le;
   if (p.N == 196 && g.K0 == 112 && g.p1_col == 208)
-    spatial_attention_split_sm100_kernel<true><<<grid, SP2_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p, g);
+    le = launch_kernel_pdl(spatial_attention_split_sm100_kernel<true>, dim3(grid), dim3(SP2_THREADS), smem, st, tmIn, tmOutA,
+                           tmOutB, p, g);
   else
-    spatial_attention_split_sm100_kernel<false><<<grid, SP2_THREADS, smem, st>>>(tmIn, tmOutA, tmOutB, p, g);
+    le = launch_kernel_pdl(spatial_attention_split_sm100_kernel<false>, dim3(grid), dim3(SP2_THREADS), smem, st, tmIn, tmOutA,
+                           tmOutB, p, g);
+  if (le != cudaSuccess) return set_error("attention(split sm100) launch: %s", cudaGetErrorString(le));
   return 0;
 }
 

@@ -21,6 +21,29 @@ template <class T> struct PerDevice {
   T& get() { return v[device_slot()]; }
 };
 
+// Programmatic dependent launch for the kernels of the forward's hot path (GEMMs, fused temporal kernel, spatial attention +
+// fix-up, cls_mean, row_offsets): 1 launches them with cudaLaunchAttributeProgrammaticStreamSerialization, so a
+// kernel's prologue overlaps the tail of its predecessor; each of those kernels executes griddepcontrol.wait before it touches
+// global memory.  0 (default) = ordinary launches.
+int pdl_enabled();
+void set_pdl(int on);
+// kernel<<<grid, block, smem, st>>>(args...) with the attribute when enabled
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Optional live per-kernel timing (CUDA events on the launching stream), used by bench.py for the roofline figures.
 // PROF_GEMM_HBM: short-K (K <= 1024) deferred-LayerNorm producer GEMMs - bounded by their residual / output streams (work is
 // counted in bytes), unlike every other GEMM launch (tensor bound, work in FLOPs).

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(256) rowstats768_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) row_offsets768_kernel(const float* __restrict__ stats, float* __restrict__ xoff,
                                                              long long M) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long row = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (row >= M) return;
   const float4* sp = reinterpret_cast<const float4*>(stats) + row * 3;
@@ -243,6 +245,8 @@ __global__ void broadcast_row768_kernel(const float* __restrict__ src, float* __
 // linear so the mean is taken BEFORE attn.proj).  Output bf16 (+ lo).
 __global__ void cls_mean_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long ldo, int split,
                                 long long lo_off, long long B, int T, float* __restrict__ out_f32) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= B * D) return;
   const long long b = idx / D;
@@ -401,7 +405,7 @@ int launch_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, 
 int launch_row_offsets768(const float* stats, float* xoff, long long M, cudaStream_t st) {
   if (M <= 0) return 0;
   ProfScope prof(PROF_LAYERNORM, static_cast<double>(M) * 52.0, st);
-  row_offsets768_kernel<<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(stats, xoff, M);
+  launch_kernel_pdl(row_offsets768_kernel, dim3(static_cast<unsigned>((M + 255) / 256)), dim3(256), 0, st, stats, xoff, M);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("row_offsets launch failed");
 }
@@ -471,8 +475,8 @@ int launch_broadcast_row768(const float* src, float* dst, long long ldd, int nro
 int launch_cls_mean(const float* in, void* out, long long ldo, int split, long long lo_off, long long B, int T,
                     float* out_f32, cudaStream_t st) {
   if (B <= 0) return 0;
-  cls_mean_kernel<<<static_cast<unsigned>((B * D + 255) / 256), 256, 0, st>>>(
-      in, reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, out_f32);
+  launch_kernel_pdl(cls_mean_kernel, dim3(static_cast<unsigned>((B * D + 255) / 256)), dim3(256), 0, st, in,
+                    reinterpret_cast<__nv_bfloat16*>(out), ldo, split, lo_off, B, T, out_f32);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("cls_mean launch failed");
 }

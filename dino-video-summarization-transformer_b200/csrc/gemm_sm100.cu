@@ -225,6 +225,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (kCG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // nothing above touched global memory: the prologue may overlap the previous kernel's tail
+  pdl_launch_dependents();
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int tile0 = kCG == 2 ? blockIdx.x / 2 : blockIdx.x;
@@ -707,13 +709,15 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const bool hbm_bound = kOut == 3 && g.K <= 1024;
   const double hbm_bytes = static_cast<double>(g.M) * (2.0 * g.K + 10.0 * g.N) + 2.0 * g.N * g.K;  // A, x in / out, xb, W
   ProfScope prof(hbm_bound ? PROF_GEMM_HBM : PROF_GEMM,

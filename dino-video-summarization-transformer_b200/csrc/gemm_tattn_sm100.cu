@@ -149,6 +149,8 @@ gemm_ln_tattn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // nothing above touched global memory: the prologue may overlap the previous kernel's tail
+  pdl_launch_dependents();
 
   constexpr int NUM_HEADS = 12;
   const int num_tiles = p.num_m_blocks * NUM_HEADS;
@@ -521,13 +523,15 @@ static int launch_tattn_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ProfScope prof(PROF_GEMM_TATTN, flops, stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_ln_tattn_kernel<MAXP>, tmA, tmB, tmO, p);
   if (e != cudaSuccess) return set_error("gemm_ln_tattn launch: %s", cudaGetErrorString(e));

@@ -29,6 +29,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream still runs (as that kernel's CTAs leave their SMs) and run its
+// prologue - barrier init, TMEM allocation, descriptor prefetch; pdl_wait() then blocks until the predecessor has completed
+// and its memory is visible, so EVERY global-memory access of the kernel must come after it.  pdl_launch_dependents() right
+// after it lets the successor do the same with this kernel.  Both are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -64,6 +64,10 @@ void dvst_set_ln_fusion(int on);
  * and the temporal attention kernel separately.  For T in {16, 32, 64} both forms give the same bits. */
 void dvst_set_temporal_fusion(int on);
 
+/* Tuning / test hook: 1 launches the forward's hot-path kernels with programmatic dependent launch (a kernel's prologue
+ * overlaps the tail of its predecessor; results are identical), 0 (default) uses ordinary stream-ordered launches. */
+void dvst_set_pdl(int on);
+
 /* L2-residency tuning: walk a batch in chunks of about `rows` token rows (0 = whole batch per pass).  Results are
  * bit-identical for any value (rows of every kernel are independent).  Call before dvst_workspace_bytes. */
 void dvst_set_chunk_rows(long long rows);
