@@ -106,7 +106,7 @@ int launch_layernorm768(const float* x, long long ldx, const float* gamma, const
 // no residual GEMM has written yet (CLS rows after embedding).
 // xoff (optional): receives the exact row mean; xb and the statistics are then those of x - mean
 int launch_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M,
-                       cudaStream_t st, float* xoff = nullptr);
+                       cudaStream_t st, float* xoff = nullptr, long long lo_off = 0);  // lo_off > 0: xb = [hi | lo]
 // xoff[r] += mean of the centred row (sum of the six per-128-column sums / 768): moves the offsets to the current row means
 int launch_row_offsets768(const float* stats, float* xoff, long long M, cudaStream_t st);
 int launch_im2col16(const float* x, void* out, long long ldo, int split, long long lo_off, int B, int T, int H, int W,

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restri
 __global__ void __launch_bounds__(256) rowstats768_kernel(const float* __restrict__ x, long long ldx,
                                                           __nv_bfloat16* __restrict__ xb, long long ldxb,
                                                           float* __restrict__ stats, long long M,
-                                                          float* __restrict__ xoff) {
+                                                          float* __restrict__ xoff, long long lo_off) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(256) rowstats768_kernel(const float* __restric
     s2 = warp_sum(s2);
     if (lane == 0) *reinterpret_cast<float2*>(stats + (row * 6 + j) * 2) = make_float2(s1, s2);
     *reinterpret_cast<uint2*>(xb + row * ldxb + (j * 32 + lane) * 4) = make_uint2(pack2(c.x, c.y), pack2(c.z, c.w));
+    if (lo_off > 0)  // split precision: xb = [hi | lo]
+      *reinterpret_cast<uint2*>(xb + row * ldxb + lo_off + (j * 32 + lane) * 4) =
+          make_uint2(pack2(c.x - bf16_round(c.x), c.y - bf16_round(c.y)), pack2(c.z - bf16_round(c.z), c.w - bf16_round(c.w)));
   }
 }
 
@@ -393,11 +396,11 @@ int launch_layernorm768(const float* x, long long ldx, const float* gamma, const
 }
 
 int launch_rowstats768(const float* x, long long ldx, void* xb, long long ldxb, float* stats, long long M,
-                       cudaStream_t st, float* xoff) {
+                       cudaStream_t st, float* xoff, long long lo_off) {
   if (M <= 0) return 0;
   ProfScope prof(PROF_LAYERNORM, static_cast<double>(M) * D * 6.0, st);
   rowstats768_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(xb), ldxb,
-                                                                        stats, M, xoff);
+                                                                        stats, M, xoff, lo_off);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : set_error("rowstats launch failed");
 }

@@ -57,13 +57,18 @@ constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
 // ahead); 5 = the short-K producers (K = 768: patch-embed, temporal proj*fc, proj), which are bound by their fp32 residual
 // stream, not by the tensor core: one operand stage is traded for two more 4 KiB boxes per warp so that the residual loads
 // run four chunks (64 KiB per CTA) ahead (ncu: 40 % of the epilogue warps' time was the wait for a residual box).
+// Split-precision producers (kOut = 4) also stage the lo half of the bf16 copy: their two 2 KiB bf16 boxes are [hi | lo] of
+// ONE chunk (single buffered - the warp waits for the previous chunk's stores before it refills them) instead of the hi boxes
+// of two chunks, so the shared-memory budget and the five operand stages stay (with four stages every three-product producer
+// launch was 5 % slower: 514 -> 610 us at K = 768, 1 892 -> 1 990 us at K = 3 072).
 template <int kCG, int kRing = 3> struct Cfg {
+  static constexpr bool DEEP = kRing > 3;
   static constexpr int B_ROWS = BN / kCG;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = kCG == 1 ? 3 : (kRing > 3 ? 4 : 5);
+  static constexpr int STAGES = kCG == 1 ? 3 : (DEEP ? 4 : 5);
   static constexpr int PRODUCER_WARP_BYTES = kRing * STG_BUF_BYTES + STG_BUF_BYTES;  // ring + two 2 KiB bf16 boxes
-  static constexpr int EPI_BYTES = kRing > 3 ? 4 * PRODUCER_WARP_BYTES : EPI_WARPS * STG_BYTES;
+  static constexpr int EPI_BYTES = DEEP ? 4 * PRODUCER_WARP_BYTES : EPI_WARPS * STG_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -164,15 +169,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // kOut: 0 = bf16, 1 = fp32 (plain or reduce-add), 2 = bf16 hi/lo pair.  kAct: 0 = none, 1 = exact-erf GELU.  Compile-time
 // so the epilogue (issue-bound next to the 256x256x768 MMA of fc1) carries no predicated code of the other modes.
-// kOut = 3: fp32 in-place residual (TMA load + add + TMA store) + bf16 copy + row statistics (deferred LayerNorm producer).
-// kLN = 1: deferred LayerNorm consumer (bf16 output only).
+// kOut = 3: fp32 in-place residual (TMA load + add + TMA store) + bf16 copy + row statistics (deferred LayerNorm producer);
+// kOut = 4: the same with the copy as a bf16 [hi | lo] pair (split precision; lo at column + lo_off of xb).
+// kLN = 1: deferred LayerNorm consumer (bf16 output, or the hi/lo pair in split precision).
 template <int kCG, int kOut, int kAct, int kLN, int kRing = 3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmXb,
                     const GemmParams p) {
-  constexpr int EW = kOut == 3 ? 4 : EPI_WARPS;  // epilogue warps that take part
-  constexpr bool kProducer = kOut == 3;
+  constexpr bool kProducer = kOut == 3 || kOut == 4;
+  constexpr bool kXbLo = kOut == 4;
+  constexpr int EW = kProducer ? 4 : EPI_WARPS;  // epilogue warps that take part
   using C = Cfg<kCG, kRing>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -424,13 +431,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               unpk2(ca, w[4 * j], w[4 * j + 1]);
               unpk2(cb, w[4 * j + 2], w[4 * j + 3]);
             }
-            const uint32_t bbox = bst + (g & 1) * (STG_BUF_BYTES / 2) + brow_off;
+            const uint32_t bsrc = bst + (kXbLo ? 0u : (g & 1) * (STG_BUF_BYTES / 2));  // TMA-store source of the hi box
+            const uint32_t bbox = bsrc + brow_off;
+            if constexpr (kXbLo) {  // single-buffered [hi | lo] boxes: the previous chunk's stores must have read them
+              if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bbox + ((j ^ bsw) << 4)),
-                           "r"(pack_bf16x2(w[8 * j], w[8 * j + 1])), "r"(pack_bf16x2(w[8 * j + 2], w[8 * j + 3])),
-                           "r"(pack_bf16x2(w[8 * j + 4], w[8 * j + 5])), "r"(pack_bf16x2(w[8 * j + 6], w[8 * j + 7]))
-                           : "memory");
+            for (int j = 0; j < 4; ++j) {
+              uint32_t h4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h4[i] = pack_bf16x2(w[8 * j + 2 * i], w[8 * j + 2 * i + 1]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bbox + ((j ^ bsw) << 4)), "r"(h4[0]), "r"(h4[1]),
+                           "r"(h4[2]), "r"(h4[3]) : "memory");
+              if constexpr (kXbLo) {  // lo = bf16(c - float(hi)), second box
+                uint32_t l4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  l4[i] = pack_bf16x2(w[8 * j + 2 * i] - __uint_as_float(h4[i] << 16),
+                                      w[8 * j + 2 * i + 1] - __uint_as_float(h4[i] & 0xFFFF0000u));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bbox + STG_BUF_BYTES / 2 + ((j ^ bsw) << 4)),
+                             "r"(l4[0]), "r"(l4[1]), "r"(l4[2]), "r"(l4[3]) : "memory");
+              }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (elect_one()) {
@@ -438,8 +461,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(ring + sl * STG_BUF_BYTES), "r"(gcol0), "r"(grow)
                            : "memory");
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                           ::"l"(reinterpret_cast<uint64_t>(&tmXb)), "r"(bst + (g & 1) * (STG_BUF_BYTES / 2)), "r"(gcol0),
-                             "r"(grow) : "memory");
+                           ::"l"(reinterpret_cast<uint64_t>(&tmXb)), "r"(bsrc), "r"(gcol0), "r"(grow) : "memory");
+              if constexpr (kXbLo)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmXb)),
+                               "r"(bsrc + STG_BUF_BYTES / 2), "r"(gcol0 + p.lo_off), "r"(grow) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               // the stores of the previous chunk have finished reading their boxes: its ring slot takes the load that
               // runs kRing - 1 chunks ahead, its bf16 box is the next chunk's
@@ -689,8 +715,10 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   const bool f32out = g.out_kind == 1 || g.out_kind == 3;
   if (int rc = make_tmap_2d(&tmO, g.out, f32out ? 4 : 2, g.M, out_cols, g.ldo, 32, f32out ? 32 : 64)) return rc;
   CUtensorMap tmXb = tmO;
-  if (kOut == 3)
-    if (int rc = make_tmap_2d(&tmXb, g.xb, 2, g.M, g.N, g.ldxb, 32, 32, true)) return rc;
+  if (kOut == 3 || kOut == 4)
+    if (int rc = make_tmap_2d(&tmXb, g.xb, 2, g.M, kOut == 4 ? static_cast<uint64_t>(g.lo_off) + g.N : g.N, g.ldxb, 32, 32,
+                              true))
+      return rc;
 
   GemmParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.split = g.split;
@@ -718,7 +746,7 @@ static int launch_gemm_impl(const GemmArgs& g, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  const bool hbm_bound = kOut == 3 && g.K <= 1024;
+  const bool hbm_bound = kOut == 3 && g.K <= 1024;   // (the three-product split producers, kOut = 4, are tensor bound)
   const double hbm_bytes = static_cast<double>(g.M) * (2.0 * g.K + 10.0 * g.N) + 2.0 * g.N * g.K;  // A, x in / out, xb, W
   ProfScope prof(hbm_bound ? PROF_GEMM_HBM : PROF_GEMM,
                  hbm_bound ? hbm_bytes : 2.0 * g.M * g.N * g.K * (g.split ? 3.0 : 1.0), stream);
@@ -743,25 +771,33 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     return set_error("gemm: the fused residual add is in place (residual must alias the fp32 output)");
   if (g.out_kind == 3) {
     // deferred-LayerNorm producer: x += A W^T + b in place, xb = bf16(x), stats[row][n_block] = (sum, sumsq)
-    if (g.residual == nullptr || g.xb == nullptr || g.stats_out == nullptr || g.act != 0 || g.split != 0)
-      return set_error("gemm: out_kind 3 needs residual (in place), xb, stats_out, no activation, bf16 precision");
+    if (g.residual == nullptr || g.xb == nullptr || g.stats_out == nullptr || g.act != 0)
+      return set_error("gemm: out_kind 3 needs residual (in place), xb, stats_out, no activation");
+    if (g.split != 0 && (g.lo_off < g.N || g.lo_off + g.N > g.ldxb))
+      return set_error("gemm: split-precision out_kind 3 writes xb as [hi | lo]: N <= lo_off <= ldxb - N");
     if ((reinterpret_cast<uintptr_t>(g.xb) & 15) || (g.ldxb % 8) || (reinterpret_cast<uintptr_t>(g.stats_out) & 15))
       return set_error("gemm: xb and stats must be 16-byte aligned, ldxb a multiple of 8");
   }
   if (g.ln_stats != nullptr) {
-    if (g.out_kind != 0 || g.K != 768 || g.ln_colsum == nullptr || g.split != 0 ||
+    if (g.out_kind != (g.split ? 2 : 0) || g.K != 768 || g.ln_colsum == nullptr ||
         (reinterpret_cast<uintptr_t>(g.ln_stats) & 15) || (reinterpret_cast<uintptr_t>(g.ln_colsum) & 15))
-      return set_error("gemm: deferred LayerNorm needs bf16 output, K = 768, a column-sum vector, bf16 precision");
+      return set_error("gemm: deferred LayerNorm needs K = 768, a column-sum vector and bf16 output (the hi/lo pair in "
+                       "split precision)");
   }
   // small problems (fewer 256-row tiles than SM pairs would leave half the chip idle) stay on the 1-CTA kernel
   const long long tiles2 = static_cast<long long>((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   if (g.act < 0 || g.act > 1) return set_error("gemm: bad act %d", g.act);
   const bool cg2 = g_gemm_cta_group == 2 && tiles2 >= num_sms() / 2;
   if (g.ln_stats != nullptr) {
+    if (g.split) {
+      if (g.act == 0) return cg2 ? launch_gemm_impl<2, 2, 0, 1>(g, stream) : launch_gemm_impl<1, 2, 0, 1>(g, stream);
+      return cg2 ? launch_gemm_impl<2, 2, 1, 1>(g, stream) : launch_gemm_impl<1, 2, 1, 1>(g, stream);
+    }
     if (g.act == 0) return cg2 ? launch_gemm_impl<2, 0, 0, 1>(g, stream) : launch_gemm_impl<1, 0, 0, 1>(g, stream);
     return cg2 ? launch_gemm_impl<2, 0, 1, 1>(g, stream) : launch_gemm_impl<1, 0, 1, 1>(g, stream);
   }
   if (g.out_kind == 3) {
+    if (g.split) return cg2 ? launch_gemm_impl<2, 4, 0, 0>(g, stream) : launch_gemm_impl<1, 4, 0, 0>(g, stream);
     if (!cg2) return launch_gemm_impl<1, 3, 0, 0>(g, stream);
     // short K: bound by the residual stream - deeper residual prefetch, one operand stage fewer
     return (g.K <= 1024 && g_producer_ring > 3) || g_producer_ring == 6 ? launch_gemm_impl<2, 3, 0, 0, 5>(g, stream)

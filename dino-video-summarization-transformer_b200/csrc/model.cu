@@ -34,8 +34,9 @@ struct BlockW {
              *fc2_w = nullptr;
   const float *tqkv_b = nullptr, *tproj_b = nullptr, *qkv_b = nullptr, *proj_b = nullptr, *fc1_b = nullptr,
               *fc2_b = nullptr;
-  // deferred LayerNorm (optional, bf16 precision): W' = bf16(gamma * W), colsum(W'), b + W beta for the three Linears
-  // that consume a LayerNorm output (temporal qkv <- temporal_norm1, qkv <- norm1, fc1 <- norm2)
+  // deferred LayerNorm (optional): W' = bf16(gamma * W) (split precision: the [hi | lo] pair of gamma * W), colsum(W'),
+  // b + W beta for the three Linears that consume a LayerNorm output (temporal qkv <- temporal_norm1, qkv <- norm1,
+  // fc1 <- norm2)
   const void *tqkv_wf = nullptr, *qkv_wf = nullptr, *fc1_wf = nullptr;
   const float *tqkv_sf = nullptr, *tqkv_bf = nullptr, *qkv_sf = nullptr, *qkv_bf = nullptr, *fc1_sf = nullptr,
               *fc1_bf = nullptr;
@@ -64,7 +65,7 @@ struct Workspace {
   float* cls_acc;
   float* emb;
   float* tmp;  // [rows, 768] fp32 scratch for space_only's frame mean
-  void* xb;     // bf16 [M, 768] copy of x (deferred LayerNorm: the A operand of the consuming GEMM)
+  void* xb;     // bf16 [M, 768 k] copy of x (deferred LayerNorm: the A operand of the consuming GEMM; k = 2: [hi | lo])
   float* stats; // fp32 [M, 6, 2] per-128-column (sum, sumsq) of every row of x
   float* xoff;  // fp32 [M] per-row offsets of xb (xb = bf16(x - xoff)), refreshed once per block
   void* attn_scratch;  // fix-up list of the one-pass spatial softmax
@@ -93,8 +94,8 @@ static Workspace carve(const Model& m, void* base, long long B, int T, int gh, i
   w.emb = static_cast<float*>(take(static_cast<size_t>(N) * T * D * 4));
   w.tmp = static_cast<float*>(take(m.cfg.attention_type == DVST_ATTN_SPACE_ONLY
                                        ? static_cast<size_t>(B) * (N + 1) * D * 4 : 1024));
-  const bool fl = m.fused_ln && m.cfg.precision == DVST_PRECISION_BF16;
-  w.xb = take(fl ? static_cast<size_t>(M) * D * 2 : 1024);
+  const bool fl = m.fused_ln;
+  w.xb = take(fl ? static_cast<size_t>(M) * D * 2 * k : 1024);
   w.stats = static_cast<float*>(take(fl ? static_cast<size_t>(M) * 12 * 4 : 1024));
   w.xoff = static_cast<float*>(take(fl ? static_cast<size_t>(M) * 4 : 1024));
   w.attn_scratch_bytes = m.cfg.attention_type == DVST_ATTN_JOINT
@@ -176,8 +177,8 @@ int dvst_finalize_weights(dvst_model* h) {
     auto it = m->named.find(k);
     return it == m->named.end() ? nullptr : it->second;
   };
-  bool all = m->cfg.precision == DVST_PRECISION_BF16;
-  bool all_perm = divided;
+  bool all = true;
+  bool all_perm = divided && m->cfg.precision == DVST_PRECISION_BF16;  // the fused temporal kernel is bf16 only
   for (int i = 0; i < m->cfg.depth; ++i) {
     const std::string p = "blocks." + std::to_string(i) + ".";
     BlockW& b = m->blocks[i];
@@ -338,26 +339,28 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
   auto ln = [&](const float* src, const float* gw_, const float* gb_, long long rows) {
     return launch_layernorm768(src, D, gw_, gb_, w.a, lda, act_kind, D, rows, LN_EPS, st);
   };
-  // Deferred LayerNorm (bf16 precision, folded tensors present): residual GEMMs also emit xb = bf16(x) and the row
-  // statistics, the GEMMs that consume LayerNorm(x) run on xb with gamma folded into their weights (gemm_sm100.cu).
-  const bool fl = m->fused_ln && g_ln_fusion && !split;
+  // Deferred LayerNorm (folded tensors present): residual GEMMs also emit xb = bf16(x) (split precision: its [hi | lo]
+  // pair) and the row statistics, the GEMMs that consume LayerNorm(x) run on xb with gamma folded into their weights
+  // (gemm_sm100.cu).
+  const bool fl = m->fused_ln && g_ln_fusion;
   __nv_bfloat16* xb = static_cast<__nv_bfloat16*>(w.xb);
+  const long long ldxb = split ? 2 * D : D;
   // x[row0 .. row0+rows) += A W^T + bias, plus xb / stats of those rows
   auto gemm_res = [&](const void* A, const void* Wt, const float* bias, long long row0, long long rows, int K) {
     GemmArgs g;
-    g.A = A; g.lda = K == D ? lda : ldh; g.W = Wt; g.ldw = K; g.bias = bias;
-    g.M = static_cast<int>(rows); g.N = D; g.K = K;
+    g.A = A; g.lda = K == D ? lda : ldh; g.W = Wt; g.ldw = split ? 2LL * K : K; g.bias = bias;
+    g.M = static_cast<int>(rows); g.N = D; g.K = K; g.split = split;
     g.residual = w.x + row0 * D; g.ldr = D; g.out = w.x + row0 * D; g.ldo = D; g.out_kind = 3;
-    g.xb = xb + row0 * D; g.ldxb = D; g.stats_out = w.stats + row0 * 12; g.xoff = w.xoff + row0;
+    g.xb = xb + row0 * ldxb; g.ldxb = ldxb; g.lo_off = D; g.stats_out = w.stats + row0 * 12; g.xoff = w.xoff + row0;
     return launch_gemm(g, st);
   };
   // out[row0 .. row0+rows) = act(LayerNorm(x) W^T + b) through the folded form
   auto gemm_ln = [&](const void* Wf, const float* sf, const float* bf, long long row0, long long rows, int Nn, void* o,
                      long long ldo, int act) {
     GemmArgs g;
-    g.A = xb + row0 * D; g.lda = D; g.W = Wf; g.ldw = D; g.bias = bf;
-    g.M = static_cast<int>(rows); g.N = Nn; g.K = D;
-    g.out = o; g.ldo = ldo; g.out_kind = 0; g.act = act;
+    g.A = xb + row0 * ldxb; g.lda = ldxb; g.W = Wf; g.ldw = ldxb; g.bias = bf;
+    g.M = static_cast<int>(rows); g.N = Nn; g.K = D; g.split = split;
+    g.out = o; g.ldo = ldo; g.out_kind = act_kind; g.lo_off = ldo / 2; g.act = act;
     g.ln_stats = w.stats + row0 * 12; g.ln_colsum = sf; g.ln_eps = LN_EPS;
     return launch_gemm(g, st);
   };
@@ -376,7 +379,9 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
     DVST_TRY(gemm_res(w.a, m->pe_w, m->pe_b, 0, Mt, D));
   } else DVST_TRY(gemm(w.a, lda, m->pe_w, m->pe_b, Mt, D, D, w.x, w.x, D, 1, 0));
   DVST_TRY(launch_broadcast_row768(m->cls_pos0, w.x + Mt * D, D, static_cast<int>(n_cls), st));
-  if (fl) DVST_TRY(launch_rowstats768(w.x + Mt * D, D, xb + Mt * D, D, w.stats + Mt * 12, n_cls, st, w.xoff + Mt));
+  if (fl)
+    DVST_TRY(launch_rowstats768(w.x + Mt * D, D, xb + Mt * ldxb, ldxb, w.stats + Mt * 12, n_cls, st, w.xoff + Mt,
+                                split ? D : 0));
 
   for (int i = 0; i < m->cfg.depth; ++i) {
     const BlockW& b = m->blocks[i];
@@ -426,7 +431,7 @@ static int forward_chunk(dvst_model* h, const float* x_in, const int* starts, in
       __nv_bfloat16* qkv_bf = static_cast<__nv_bfloat16*>(w.qkv);
       __nv_bfloat16* a_bf = static_cast<__nv_bfloat16*>(w.a);
       if (fl) {
-        DVST_TRY(gemm_ln(static_cast<const __nv_bfloat16*>(b.qkv_wf) + D * D, b.qkv_sf + D, b.qkv_bf + D, 0, Mt, 2 * D,
+        DVST_TRY(gemm_ln(static_cast<const __nv_bfloat16*>(b.qkv_wf) + D * wrow, b.qkv_sf + D, b.qkv_bf + D, 0, Mt, 2 * D,
                          qkv_bf + D, ldq, 0));
         DVST_TRY(gemm_ln(b.qkv_wf, b.qkv_sf, b.qkv_bf, Mt, n_cls, 3 * D, qkv_bf + Mt * ldq, ldq, 0));
       } else {

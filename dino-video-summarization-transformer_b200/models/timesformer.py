@@ -227,29 +227,31 @@ class VisionTransformer(nn.Module):
             pk[p + "mlp.fc1.b"] = f32(blk.mlp.fc1.bias)
             pk[p + "mlp.fc2.w"] = self._gemm_weight(blk.mlp.fc2.weight, device)
             pk[p + "mlp.fc2.b"] = f32(blk.mlp.fc2.bias)
-        if self.precision == "bf16":
-            # Deferred LayerNorm (csrc/gemm_sm100.cu): LN(x) W^T + b = rstd (x W'^T) - rstd mean colsum(W') + (b + W beta)
-            # with W' = bf16(gamma * W); composed in fp64.  The GEMM then runs on bf16(x) and the stand-alone
-            # LayerNorm pass disappears.
-            def fold(lin, norm, name):
-                W = lin.weight.detach().to(device).double()
-                g = norm.weight.detach().to(device).double()
-                beta = norm.bias.detach().to(device).double()
-                wf = (W * g[None, :]).float().to(torch.bfloat16).contiguous()
-                pk[name + ".wf"] = wf
-                pk[name + ".sf"] = wf.double().sum(1).float().contiguous()
-                pk[name + ".bf"] = (lin.bias.detach().to(device).double() + W @ beta).float().contiguous()
-            # head-major row order of the temporal qkv tensors for the fused qkv-GEMM + temporal-attention kernel
-            # (csrc/gemm_tattn_sm100.cu): one 192-row block per head = [q_h | k_h | v_h]
-            hp = torch.arange(2304, device=device).view(3, 12, 64).permute(1, 0, 2).reshape(-1)
-            for i, blk in enumerate(self.blocks):
-                p = f"blocks.{i}."
-                if self.attention_type == 'divided_space_time':
-                    fold(blk.temporal_attn.qkv, blk.temporal_norm1, p + "temporal_attn.qkv")
+        # Deferred LayerNorm (csrc/gemm_sm100.cu): LN(x) W^T + b = rstd (x W'^T) - rstd mean colsum(W') + (b + W beta)
+        # with W' = bf16(gamma * W) - in "high" precision the [hi | lo] pair of gamma * W, colsum that of hi + lo;
+        # composed in fp64.  The GEMM then runs on the bf16 copy of x its producer left (hi / lo pair in "high") and the
+        # stand-alone LayerNorm pass disappears.
+        def fold(lin, norm, name):
+            W = lin.weight.detach().to(device).double()
+            g = norm.weight.detach().to(device).double()
+            beta = norm.bias.detach().to(device).double()
+            wf = self._gemm_weight((W * g[None, :]).float(), device)
+            pk[name + ".wf"] = wf
+            K = W.shape[1]
+            pk[name + ".sf"] = (wf[:, :K].double() + (wf[:, K:].double() if wf.shape[1] > K else 0.0)).sum(1).float().contiguous()
+            pk[name + ".bf"] = (lin.bias.detach().to(device).double() + W @ beta).float().contiguous()
+        # head-major row order of the temporal qkv tensors for the fused qkv-GEMM + temporal-attention kernel
+        # (csrc/gemm_tattn_sm100.cu, bf16 precision): one 192-row block per head = [q_h | k_h | v_h]
+        hp = torch.arange(2304, device=device).view(3, 12, 64).permute(1, 0, 2).reshape(-1)
+        for i, blk in enumerate(self.blocks):
+            p = f"blocks.{i}."
+            if self.attention_type == 'divided_space_time':
+                fold(blk.temporal_attn.qkv, blk.temporal_norm1, p + "temporal_attn.qkv")
+                if self.precision == "bf16":
                     for sfx in ("wf", "sf", "bf"):
                         pk[p + "temporal_attn.qkv." + sfx + "p"] = pk[p + "temporal_attn.qkv." + sfx][hp].contiguous()
-                fold(blk.attn.qkv, blk.norm1, p + "attn.qkv")
-                fold(blk.mlp.fc1, blk.norm2, p + "mlp.fc1")
+            fold(blk.attn.qkv, blk.norm1, p + "attn.qkv")
+            fold(blk.mlp.fc1, blk.norm2, p + "mlp.fc1")
         P = int(round(math.sqrt(self.pos_embed.shape[1] - 1)))
         cfg = _Config(self.depth, self.time_embed.shape[1] if self.attention_type != 'space_only' else 1, P,
                       _ATTN[self.attention_type], _PRECISION[self.precision])

@@ -55,7 +55,7 @@ void dvst_set_producer_ring(int boxes);
  * 0 forces the mma.sync kernels for every mode. */
 void dvst_set_attention_impl(int impl);
 
-/* Tuning / test hook: 1 (default) lets bf16-precision models whose folded tensors are registered run the deferred
+/* Tuning / test hook: 1 (default) lets models whose folded tensors are registered run the deferred
  * LayerNorm path (see dvst_gemm_bf16_ln); 0 forces the stand-alone LayerNorm kernel.  Call before dvst_workspace_bytes. */
 void dvst_set_ln_fusion(int on);
 
