@@ -545,6 +545,31 @@ def test_attention_high_precision_tcgen05(dev, mode, B, T, N, impl):
     assert worst < 1e-4, worst
 
 
+@pytest.mark.parametrize("B,T,N", [(2, 16, 9), (1, 3, 50), (1, 30, 7), (1, 1, 3), (3, 32, 5), (1, 48, 3), (1, 60, 2),
+                                   (4, 16, 196)])
+def test_temporal_attention_high_precision(dev, B, T, N):
+    """Split-precision temporal attention (mode 0, bf16 hi / lo operands, every product hi*hi + hi*lo + lo*hi, P split the same
+    way; csrc/attention.cu attention_kernel<1, true>) against fp64 torch on the same operands."""
+    torch.manual_seed(70 + T)
+    L = _lib.lib()
+    Mt = B * N * T
+    x = torch.randn(Mt + B, 2304, device=dev) * 1.5
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    qkv = torch.cat([hi, lo], 1).contiguous()
+    xe = hi.double() + lo.double()
+    out = torch.zeros(Mt + B, 1536, device=dev, dtype=torch.bfloat16)
+    _lib.check(L.dvst_attention_hp(_lib.ptr(qkv), 4608, _lib.ptr(out), 1536, None, 0, B, T, N, Mt, None, 0,
+                                   _lib.cur_stream()))
+    torch.cuda.synchronize()
+    outs = [out]
+    assert float(outs[0][Mt:].float().abs().sum()) == 0          # CLS rows are not part of the temporal attention
+    got = outs[0][:Mt, :768].double() + outs[0][:Mt, 768:].double()
+    q, k, v = (xe[:Mt, i * 768:(i + 1) * 768].reshape(B * N, T, 12, 64).transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(2, 3) * 0.125, -1) @ v).transpose(1, 2).reshape(Mt, 768)
+    assert ((got - ref).norm() / ref.norm()).item() < 1e-4
+
+
 # ---- temporal half of a divided block in one kernel: deferred-LayerNorm qkv GEMM + temporal attention out of shared memory
 @pytest.mark.parametrize("T,n_seq,clip_seqs", [(16, 313, 0), (16, 8, 0), (32, 77, 0), (64, 9, 0), (8, 401, 0), (4, 1000, 0),
                                                (1, 300, 0), (30, 131, 0), (3, 1571, 0), (5, 52, 0), (17, 40, 0), (48, 7, 0),
