@@ -15,7 +15,7 @@
 //   warps 4..11 : epilogue                      - tcgen05.ld 32x32b.x32 -> bias / GELU / dtype -> swizzled smem box ->
 //                                                 TMA store (bf16, fp32, hi/lo pair) or TMA reduce-add (fused residual)
 //
-// Deferred LayerNorm (bf16 precision): a residual GEMM (kOut = 3) reads the fp32 residual tile through TMA, adds,
+// Deferred LayerNorm: a residual GEMM (kOut = 3) reads the fp32 residual tile through TMA, adds,
 // stores the new fp32 stream AND its bf16 copy `xb`, and leaves per-row partial (sum, sum of squares) of the new row in
 // `stats[row][128-column block]`; the GEMM that consumes LayerNorm(x) (kLN = 1) then runs on `xb` with gamma folded into W:
 //   LN(x) W^T + b = rstd_r (xb W'^T)[r,c] - rstd_r mean_r colsum(W')[c] + (b + W beta)[c],   W' = bf16(gamma * W)
@@ -27,7 +27,9 @@
 //
 // `split` mode: A and W hold [hi | lo] bf16 halves along K (lo at column offset K); the K loop then runs the three
 // products hi*hi, hi*lo, lo*hi into the same accumulator (~16 mantissa bits) - the "precision=high" path that
-// reference-exact scoring (dino_similarity.py:59-63, tau_t = 0.02) needs.
+// reference-exact scoring (dino_similarity.py:59-63, tau_t = 0.02) needs.  The deferred LayerNorm runs in split mode too:
+// producers (kOut = 4) store xb as the [hi | lo] pair of x - m_r, consumers (kLN = 1, kOut = 2) fold the normalisation
+// around the three-product accumulator with colsum = row sums of W'_hi + W'_lo.
 #include "dvst_internal.h"
 #include "ptx.cuh"
 
