@@ -230,3 +230,33 @@ def test_fused_temporal_kernel_tile_geometry():
     for T in (0, 65, 1000):
         assert L.dvst_temporal_tile_geometry(T, ctypes.byref(R), ctypes.byref(KB)) != 0
         assert b"not covered" in L.dvst_last_error()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "high"])
+def test_weight_packing_folds_layernorm_into_the_consumers(prec):
+    """Packing (no GPU needed: the handle only records pointers) registers, for the three Linears that consume a LayerNorm
+    (temporal qkv, qkv, fc1), W' = gamma * W in the GEMM operand format of the precision (bf16, or the [hi | lo] pair),
+    colsum(W') and b + W beta - the tensors of the deferred LayerNorm (csrc/gemm_sm100.cu) - and folds
+    temporal_fc(temporal_attn.proj(.)) into one 768 x 768 Linear (models/timesformer.py:83,133)."""
+    m = VisionTransformer(num_classes=0, depth=1, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                          num_frames=8, precision=prec)
+    m.load_state_dict(synth_backbone_state_dict(3, depth=1, num_frames=8), strict=True)
+    m._ensure_packed(torch.device("cpu"))
+    pk, blk = m._packed, m.blocks[0]
+    k = 2 if prec == "high" else 1
+    for name, lin, norm in (("temporal_attn.qkv", blk.temporal_attn.qkv, blk.temporal_norm1),
+                            ("attn.qkv", blk.attn.qkv, blk.norm1), ("mlp.fc1", blk.mlp.fc1, blk.norm2)):
+        wf, sf, bf = (pk[f"blocks.0.{name}.{s}"] for s in ("wf", "sf", "bf"))
+        W, g, beta = lin.weight.detach().double(), norm.weight.detach().double(), norm.bias.detach().double()
+        assert wf.dtype == torch.bfloat16 and wf.shape == (W.shape[0], 768 * k)
+        w_eff = wf[:, :768].double() + (wf[:, 768:].double() if k == 2 else 0.0)      # what the tensor core multiplies by
+        rel = ((w_eff - W * g[None]).norm() / (W * g[None]).norm()).item()
+        assert rel < (2e-5 if k == 2 else 4e-3), rel                                    # 16 vs 8 significand bits
+        assert torch.allclose(sf.double(), w_eff.sum(1), rtol=0, atol=1e-5)             # colsum of the ROUNDED operand
+        assert torch.allclose(bf.double(), lin.bias.detach().double() + W @ beta, rtol=0, atol=1e-6)
+    # the head-permuted copies of the fused temporal kernel exist in bf16 precision only
+    assert ("blocks.0.temporal_attn.qkv.wfp" in pk) == (prec == "bf16")
+    wfc, wp = blk.temporal_fc.weight.detach().double(), blk.temporal_attn.proj.weight.detach().double()
+    w = pk["blocks.0.temporal_projfc.w"]
+    w_eff = w[:, :768].double() + (w[:, 768:].double() if k == 2 else 0.0)
+    assert ((w_eff - wfc @ wp).norm() / (wfc @ wp).norm()).item() < (2e-5 if k == 2 else 4e-3)
