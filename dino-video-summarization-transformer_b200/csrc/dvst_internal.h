@@ -68,13 +68,13 @@ struct GemmArgs {
   void* out = nullptr;
   long long ldo = 0;
   int out_kind = 0;  // 0 bf16, 1 fp32, 2 bf16 hi/lo pair, 3 fp32 in-place residual + bf16 copy `xb` + row stats
-  long long lo_off = 0;
-  // deferred LayerNorm (gemm_sm100.cu): consumer side (out_kind 0, K = 768) ...
+  long long lo_off = 0;  // out_kind 2: column offset of the lo half of `out`; out_kind 3 with split: ... of `xb`
+  // deferred LayerNorm (gemm_sm100.cu): consumer side (K = 768; out_kind 0, or 2 in split precision) ...
   const float* ln_stats = nullptr;   // fp32 [M, 6, 2] per-128-column (sum, sumsq) of the row A was cast from
   const float* ln_colsum = nullptr;  // fp32 [N] row sums of the gamma-folded bf16 weight
   float ln_eps = 1e-6f;
   // ... and producer side (out_kind 3, N = 768)
-  void* xb = nullptr;                // bf16 [M, ldxb]
+  void* xb = nullptr;                // bf16 [M, ldxb] (split: [hi | lo], lo at column lo_off)
   long long ldxb = 0;
   float* stats_out = nullptr;        // fp32 [M, N / 128, 2]
   // producer: per-row offset m_r; xb = bf16(x - m_r) and the statistics are those of x - m_r (null = 0)
